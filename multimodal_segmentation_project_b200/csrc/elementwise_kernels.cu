@@ -1,0 +1,775 @@
+// elementwise_kernels.cu — HBM-bound pieces of the U-Net block around the convolutions:
+// layout conversion, BatchNorm3d statistics / finalize / apply (+ReLU +Dropout3d) forward and
+// backward, MaxPool3d(2,2), nearest resize, global average pool, fused AdamW.
+//
+// Reference call sites: models/unet.py:12-14,16-18 (BN, ReLU, Dropout3d), :40,71 (MaxPool3d),
+// :81-83 (F.interpolate), models/unet_dann.py:79 (GAP), train_unet.py:226,378 (AdamW).
+// All activations are rows of C channels (NDHWC); every thread moves 8 channels (16 B bf16 /
+// 32 B fp32) per access so that warps read and write whole 128 B lines.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxPartialBlocks = 592;  // 4 CTAs per SM
+
+// ------------------------------------------------------------------ layout conversion
+template <typename T>
+__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int64_t N, int64_t C, int64_t S) {
+  // tile transpose [C, S] -> [S, C] per sample through shared memory
+  __shared__ float tile[32][33];
+  const int64_t n = blockIdx.z;
+  const int64_t s0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t c = c0 + i, s = s0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && s < S) ? x[(n * C + c) * S + s] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t s = s0 + i, c = c0 + threadIdx.x;
+    if (s < S && c < C) y[(n * S + s) * C + c] = from_f32<T>(tile[threadIdx.x][i]);
+  }
+}
+template <typename T>
+__global__ void ndhwc_to_ncdhw_kernel(const T* __restrict__ x, float* __restrict__ y, int64_t N, int64_t C, int64_t S) {
+  __shared__ float tile[32][33];
+  const int64_t n = blockIdx.z;
+  const int64_t s0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t s = s0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && s < S) ? to_f32<T>(x[(n * S + s) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t c = c0 + i, s = s0 + threadIdx.x;
+    if (s < S && c < C) y[(n * C + c) * S + s] = tile[threadIdx.x][i];
+  }
+}
+template <typename T>
+__global__ void cast_from_f32_kernel(const float* __restrict__ x, T* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = from_f32<T>(x[i]);
+}
+template <typename T>
+__global__ void cast_to_f32_kernel(const T* __restrict__ x, float* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = to_f32<T>(x[i]);
+}
+
+// ------------------------------------------------------------------ per-channel two-slot reductions
+// A block owns `rows_per_iter = kThreads / CV` rows per iteration (CV = C/8 vector columns);
+// thread (r, cv) accumulates 8 channels x 2 slots in registers, then the block reduces over r in
+// shared memory and writes partials[block][2][C].  The finalize kernels sum the blocks in fixed
+// order in fp64, so results are run-to-run deterministic.
+struct RowMap {
+  int CV, rows_per_iter, nblocks;
+};
+inline RowMap row_map(int64_t M, int C) {
+  RowMap m;
+  m.CV = C / 8;
+  m.rows_per_iter = kThreads / m.CV;
+  if (m.rows_per_iter < 1) m.rows_per_iter = 1;
+  int64_t iters = (M + m.rows_per_iter - 1) / m.rows_per_iter;
+  m.nblocks = (int)(iters < kMaxPartialBlocks ? (iters < 1 ? 1 : iters) : kMaxPartialBlocks);
+  return m;
+}
+
+template <typename F>
+__device__ __forceinline__ void block_channel_reduce(F&& body, int64_t M, int C, float* __restrict__ partials) {
+  // body(row, cv, acc0[8], acc1[8]) accumulates one row's 8 channels
+  extern __shared__ float sred[];  // [rows_per_iter][2][C]
+  const int CV = C / 8;
+  const int rows_per_iter = max(1, (int)blockDim.x / CV);
+  const int cv = threadIdx.x % CV, r = threadIdx.x / CV;
+  float a0[8], a1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
+  if (r < rows_per_iter) {
+    for (int64_t row = (int64_t)blockIdx.x * rows_per_iter + r; row < M; row += (int64_t)gridDim.x * rows_per_iter)
+      body(row, cv, a0, a1);
+  }
+  if (r < rows_per_iter) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sred[(r * 2 + 0) * C + cv * 8 + i] = a0[i];
+      sred[(r * 2 + 1) * C + cv * 8 + i] = a1[i];
+    }
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < 2 * C; q += blockDim.x) {
+    float t = 0.f;
+    for (int rr = 0; rr < rows_per_iter; ++rr) t += sred[rr * 2 * C + q];
+    partials[(int64_t)blockIdx.x * 2 * C + q] = t;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+bn_stats_kernel(const T* __restrict__ x, int64_t M, int C, float* __restrict__ partials) {
+  block_channel_reduce(
+      [&](int64_t row, int cv, float (&a0)[8], float (&a1)[8]) {
+        Vec8<T> v;
+        v.load(x + row * C + cv * 8);
+        float f[8];
+        v.get(f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a0[i] += f[i]; a1[i] = fmaf(f[i], f[i], a1[i]); }
+      },
+      M, C, partials);
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nblocks, int64_t M, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, int training, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, int64_t* __restrict__ nbt,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && nbt) nbt[0] += 1;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    double s = 0.0, ss = 0.0;
+    for (int b = 0; b < nblocks; ++b) {
+      s += (double)partials[(int64_t)b * 2 * C + c];
+      ss += (double)partials[(int64_t)b * 2 * C + C + c];
+    }
+    const double m = s / (double)M;
+    double v = ss / (double)M - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var = (float)v;
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    if (running_var) {
+      const float unbiased = (M > 1) ? (float)(v * (double)M / (double)(M - 1)) : var;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const float invstd = 1.f / sqrtf(var + eps);
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float sc = g * invstd;
+  scale[c] = sc;
+  shift[c] = b - mean * sc;
+  mean_out[c] = mean;
+  invstd_out[c] = invstd;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+bn_act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ scale,
+                  const float* __restrict__ shift, const float* __restrict__ dropmask, int relu, int64_t N, int64_t S,
+                  int C) {
+  const int CV = C / 8;
+  const int64_t total = N * S * CV;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    const int64_t row = i / CV;
+    Vec8<T> v;
+    v.load(x + row * C + cv * 8);
+    float f[8];
+    v.get(f);
+    const float4 s0 = *reinterpret_cast<const float4*>(scale + cv * 8), s1 = *reinterpret_cast<const float4*>(scale + cv * 8 + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(shift + cv * 8), h1 = *reinterpret_cast<const float4*>(shift + cv * 8 + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    const float* dm = dropmask ? dropmask + (row / S) * C + cv * 8 : nullptr;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float t = to_f32<T>(from_f32<T>(fmaf(f[k], sc[k], sh[k])));  // BN output rounded to the activation dtype
+      if (relu) t = fmaxf(t, 0.f);
+      if (dm) t *= dm[k];
+      f[k] = t;
+    }
+    v.set(f);
+    v.store(y + row * C + cv * 8);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void bn_bwd_elem(const T* __restrict__ gy, const T* __restrict__ x, int64_t row, int cv, int C,
+                                            int64_t S, const float* __restrict__ scale, const float* __restrict__ shift,
+                                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                                            const float* __restrict__ dropmask, int relu, float (&g)[8], float (&xh)[8]) {
+  Vec8<T> vg, vx;
+  vg.load(gy + row * C + cv * 8);
+  vx.load(x + row * C + cv * 8);
+  float fx[8];
+  vg.get(g);
+  vx.get(fx);
+  const float* dm = dropmask ? dropmask + (row / S) * C + cv * 8 : nullptr;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = cv * 8 + k;
+    float gg = g[k];
+    if (dm) gg *= dm[k];
+    if (relu) {
+      const float pre = to_f32<T>(from_f32<T>(fmaf(fx[k], scale[c], shift[c])));
+      if (!(pre > 0.f)) gg = 0.f;
+    }
+    g[k] = gg;
+    xh[k] = (fx[k] - mean[c]) * invstd[c];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+bn_act_bwd_reduce_kernel(const T* __restrict__ gy, const T* __restrict__ x, const float* __restrict__ scale,
+                         const float* __restrict__ shift, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, const float* __restrict__ dropmask, int relu, int64_t N,
+                         int64_t S, int C, float* __restrict__ partials) {
+  block_channel_reduce(
+      [&](int64_t row, int cv, float (&a0)[8], float (&a1)[8]) {
+        float g[8], xh[8];
+        bn_bwd_elem<T>(gy, x, row, cv, C, S, scale, shift, mean, invstd, dropmask, relu, g, xh);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a0[i] += g[i]; a1[i] = fmaf(g[i], xh[i], a1[i]); }
+      },
+      N * S, C, partials);
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int64_t M, int C,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ sums) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    s += (double)partials[(int64_t)b * 2 * C + c];
+    ss += (double)partials[(int64_t)b * 2 * C + C + c];
+  }
+  if (dbeta) dbeta[c] = (float)s;
+  if (dgamma) dgamma[c] = (float)ss;
+  sums[c] = (float)(s / (double)M);
+  sums[C + c] = (float)(ss / (double)M);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+bn_act_bwd_apply_kernel(const T* __restrict__ gy, const T* __restrict__ x, T* __restrict__ dx,
+                        const float* __restrict__ scale, const float* __restrict__ shift,
+                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                        const float* __restrict__ dropmask, int relu, const float* __restrict__ sums, int training,
+                        int64_t N, int64_t S, int C) {
+  const int CV = C / 8;
+  const int64_t total = N * S * CV;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    const int64_t row = i / CV;
+    float g[8], xh[8];
+    bn_bwd_elem<T>(gy, x, row, cv, C, S, scale, shift, mean, invstd, dropmask, relu, g, xh);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = cv * 8 + k;
+      float t = g[k];
+      if (training) t -= sums[c] + xh[k] * sums[C + c];
+      g[k] = t * scale[c];
+    }
+    Vec8<T> o;
+    o.set(g);
+    o.store(dx + row * C + cv * 8);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+channel_sum_kernel(const T* __restrict__ x, int64_t M, int C, float* __restrict__ partials) {
+  block_channel_reduce(
+      [&](int64_t row, int cv, float (&a0)[8], float (&a1)[8]) {
+        Vec8<T> v;
+        v.load(x + row * C + cv * 8);
+        float f[8];
+        v.get(f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a0[i] += f[i];
+      },
+      M, C, partials);
+}
+__global__ void channel_sum_finalize_kernel(const float* __restrict__ partials, int nblocks, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += (double)partials[(int64_t)b * 2 * C + c];
+  out[c] = (float)s;
+}
+
+// ------------------------------------------------------------------ MaxPool3d(2,2)
+__device__ __forceinline__ bool pool_better(float v, float m) { return (v > m) || (v != v); }
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int D, int H, int W, int C) {
+  const int OD = D / 2, OH = H / 2, OW = W / 2, CV = C / 8;
+  const int64_t total = (int64_t)N * OD * OH * OW * CV;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int cv = (int)(t % CV); t /= CV;
+    const int ow = (int)(t % OW); t /= OW;
+    const int oh = (int)(t % OH); t /= OH;
+    const int od = (int)(t % OD);
+    const int n = (int)(t / OD);
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int64_t row = (((int64_t)n * D + (2 * od + dz)) * H + (2 * oh + dy)) * W + (2 * ow + dx);
+          Vec8<T> v;
+          v.load(x + row * C + cv * 8);
+          float f[8];
+          v.get(f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (pool_better(f[k], m[k])) m[k] = f[k];
+        }
+    Vec8<T> o;
+    o.set(m);
+    o.store(y + ((((int64_t)n * OD + od) * OH + oh) * OW + ow) * C + cv * 8);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy, T* __restrict__ gx, int N, int D, int H, int W, int C) {
+  const int OD = D / 2, OH = H / 2, OW = W / 2, CV = C / 8;
+  const int64_t total = (int64_t)N * OD * OH * OW * CV;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int cv = (int)(t % CV); t /= CV;
+    const int ow = (int)(t % OW); t /= OW;
+    const int oh = (int)(t % OH); t /= OH;
+    const int od = (int)(t % OD);
+    const int n = (int)(t / OD);
+    float m[8];
+    int arg[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { m[k] = -INFINITY; arg[k] = 0; }
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int dz = p >> 2, dy = (p >> 1) & 1, dx = p & 1;
+      const int64_t row = (((int64_t)n * D + (2 * od + dz)) * H + (2 * oh + dy)) * W + (2 * ow + dx);
+      Vec8<T> v;
+      v.load(x + row * C + cv * 8);
+      float f[8];
+      v.get(f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (pool_better(f[k], m[k])) { m[k] = f[k]; arg[k] = p; }
+    }
+    Vec8<T> g;
+    g.load(gy + ((((int64_t)n * OD + od) * OH + oh) * OW + ow) * C + cv * 8);
+    float gf[8];
+    g.get(gf);
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int dz = p >> 2, dy = (p >> 1) & 1, dx = p & 1;
+      const int64_t row = (((int64_t)n * D + (2 * od + dz)) * H + (2 * oh + dy)) * W + (2 * ow + dx);
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (arg[k] == p) ? gf[k] : 0.f;
+      Vec8<T> ov;
+      ov.set(o);
+      ov.store(gx + row * C + cv * 8);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ nearest resize (F.interpolate default)
+__device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
+  const int s = (int)floorf((float)dst * scale);
+  return s < in_size - 1 ? s : in_size - 1;
+}
+template <typename T>
+__global__ void nearest_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int D, int H, int W, int OD, int OH,
+                                   int OW, int C) {
+  const int CV = C / 8;
+  const float sd = (float)D / OD, sh = (float)H / OH, sw = (float)W / OW;
+  const int64_t total = (int64_t)N * OD * OH * OW * CV;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int cv = (int)(t % CV); t /= CV;
+    const int ow = (int)(t % OW); t /= OW;
+    const int oh = (int)(t % OH); t /= OH;
+    const int od = (int)(t % OD);
+    const int n = (int)(t / OD);
+    const int64_t src = (((int64_t)n * D + nearest_src(od, sd, D)) * H + nearest_src(oh, sh, H)) * W + nearest_src(ow, sw, W);
+    Vec8<T> v;
+    v.load(x + src * C + cv * 8);
+    v.store(y + ((((int64_t)n * OD + od) * OH + oh) * OW + ow) * C + cv * 8);
+  }
+}
+__device__ __forceinline__ void nearest_dst_range(int src, float scale, int in_size, int out_size, int& lo, int& hi) {
+  // all dst with nearest_src(dst) == src form a contiguous range; scan a small window around src/scale
+  int guess = (int)((float)src / scale);
+  int a = guess - 2 < 0 ? 0 : guess - 2;
+  lo = out_size; hi = 0;
+  for (int d = a; d < out_size && d <= guess + 3; ++d)
+    if (nearest_src(d, scale, in_size) == src) { if (d < lo) lo = d; hi = d + 1; }
+  if (lo > hi) { lo = 0; hi = 0; }
+}
+template <typename T>
+__global__ void nearest_bwd_kernel(const T* __restrict__ gy, T* __restrict__ gx, int N, int D, int H, int W, int OD, int OH,
+                                   int OW, int C) {
+  const int CV = C / 8;
+  const float sd = (float)D / OD, sh = (float)H / OH, sw = (float)W / OW;
+  const int64_t total = (int64_t)N * D * H * W * CV;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int cv = (int)(t % CV); t /= CV;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H); t /= H;
+    const int d = (int)(t % D);
+    const int n = (int)(t / D);
+    int d0, d1, h0, h1, w0, w1;
+    nearest_dst_range(d, sd, D, OD, d0, d1);
+    nearest_dst_range(h, sh, H, OH, h0, h1);
+    nearest_dst_range(w, sw, W, OW, w0, w1);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int a = d0; a < d1; ++a)
+      for (int b = h0; b < h1; ++b)
+        for (int c = w0; c < w1; ++c) {
+          Vec8<T> v;
+          v.load(gy + ((((int64_t)n * OD + a) * OH + b) * OW + c) * C + cv * 8);
+          float f[8];
+          v.get(f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] += f[k];
+        }
+    Vec8<T> o;
+    o.set(acc);
+    o.store(gx + ((((int64_t)n * D + d) * H + h) * W + w) * C + cv * 8);
+  }
+}
+
+// ------------------------------------------------------------------ global average pool
+template <typename T>
+__global__ void gap_fwd_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t N, int64_t S, int C) {
+  // one block per (n, channel-vector); threads stride over S
+  const int CV = C / 8;
+  const int64_t n = blockIdx.x / CV;
+  const int cv = blockIdx.x % CV;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int64_t s = threadIdx.x; s < S; s += blockDim.x) {
+    Vec8<T> v;
+    v.load(x + (n * S + s) * C + cv * 8);
+    float f[8];
+    v.get(f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += f[k];
+  }
+  __shared__ float red[8][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    acc[k] = warp_sum(acc[k]);
+    if (lane == 0) red[warp][k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w][threadIdx.x];
+    out[n * C + cv * 8 + threadIdx.x] = t / (float)S;
+  }
+}
+template <typename T>
+__global__ void gap_bwd_kernel(const float* __restrict__ gout, T* __restrict__ gx, int accumulate, int64_t N, int64_t S, int C) {
+  const int CV = C / 8;
+  const int64_t total = N * S * CV;
+  const float inv = 1.f / (float)S;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    const int64_t row = i / CV;
+    const int64_t n = row / S;
+    float f[8];
+    if (accumulate) {
+      Vec8<T> v;
+      v.load(gx + row * C + cv * 8);
+      v.get(f);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] += gout[n * C + cv * 8 + k] * inv;
+    Vec8<T> o;
+    o.set(f);
+    o.store(gx + row * C + cv * 8);
+  }
+}
+
+__global__ void scale_f32_kernel(const float* __restrict__ x, float* __restrict__ out, float alpha, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = alpha * x[i];
+}
+
+// ------------------------------------------------------------------ fused AdamW over a flat buffer
+__global__ void adamw_prepare_kernel(int64_t* step, float beta1, float beta2, float* hyper) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const int64_t t = step[0] + 1;
+    step[0] = t;
+    hyper[1] = 1.f - powf(beta1, (float)t);
+    hyper[2] = 1.f - powf(beta2, (float)t);
+  }
+}
+__global__ void __launch_bounds__(kThreads)
+adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                  int64_t n, const float* __restrict__ hyper, float beta1, float beta2, float eps, float wd,
+                  float grad_scale) {
+  const float lr = hyper[0], bc1 = hyper[1], bc2 = hyper[2];
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const float decay = 1.f - lr * wd;
+  const int64_t n4 = n / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = ga[k] * grad_scale;
+      ma[k] = beta1 * ma[k] + (1.f - beta1) * gk;
+      va[k] = beta2 * va[k] + (1.f - beta2) * gk * gk;
+      const float denom = sqrtf(va[k]) * inv_sqrt_bc2 + eps;
+      pa[k] = pa[k] * decay - step_size * ma[k] / denom;
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  // tail
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gk = g[i] * grad_scale;
+    m[i] = beta1 * m[i] + (1.f - beta1) * gk;
+    v[i] = beta2 * v[i] + (1.f - beta2) * gk * gk;
+    const float denom = sqrtf(v[i]) * inv_sqrt_bc2 + eps;
+    p[i] = p[i] * decay - step_size * m[i] / denom;
+  }
+}
+
+inline int ew_grid(int64_t items) { return b200_grid_for(items, kThreads, B200_NUM_SMS * 16); }
+
+int check_rows(const char* name, int64_t M, int C) {
+  B200_REQUIRE(M > 0, B200_ERR_SHAPE, "%s: empty input (M=%lld)", name, (long long)M);
+  B200_REQUIRE(C >= 8 && C % 8 == 0 && C <= 2048, B200_ERR_UNSUPPORTED, "%s: C=%d must be a multiple of 8 in [8,2048]", name, C);
+  return B200_OK;
+}
+
+}  // namespace
+
+// =========================================================================== exports
+extern "C" int b200_ncdhw_to_ndhwc(int dtype, const float* x, void* y, int64_t N, int64_t C, int64_t S, void* stream) {
+  B200_REQUIRE(x && y && N > 0 && C > 0 && S > 0, B200_ERR_SHAPE, "ncdhw_to_ndhwc: bad arguments");
+  B200_REQUIRE(N <= 65535, B200_ERR_UNSUPPORTED, "ncdhw_to_ndhwc: N too large");
+  dim3 grid((unsigned)((S + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N), block(32, 8);
+  B200_DISPATCH_DTYPE(dtype, T, (ncdhw_to_ndhwc_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>(x, (T*)y, N, C, S)));
+  B200_CHECK_LAUNCH("ncdhw_to_ndhwc");
+  return B200_OK;
+}
+extern "C" int b200_ndhwc_to_ncdhw(int dtype, const void* x, float* y, int64_t N, int64_t C, int64_t S, void* stream) {
+  B200_REQUIRE(x && y && N > 0 && C > 0 && S > 0, B200_ERR_SHAPE, "ndhwc_to_ncdhw: bad arguments");
+  B200_REQUIRE(N <= 65535, B200_ERR_UNSUPPORTED, "ndhwc_to_ncdhw: N too large");
+  dim3 grid((unsigned)((S + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N), block(32, 8);
+  B200_DISPATCH_DTYPE(dtype, T, (ndhwc_to_ncdhw_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)x, y, N, C, S)));
+  B200_CHECK_LAUNCH("ndhwc_to_ncdhw");
+  return B200_OK;
+}
+extern "C" int b200_cast_from_f32(int dtype, const float* x, void* y, int64_t n, void* stream) {
+  B200_REQUIRE(x && y && n > 0, B200_ERR_SHAPE, "cast_from_f32: bad arguments");
+  B200_DISPATCH_DTYPE(dtype, T, (cast_from_f32_kernel<T><<<ew_grid(n), kThreads, 0, (cudaStream_t)stream>>>(x, (T*)y, n)));
+  B200_CHECK_LAUNCH("cast_from_f32");
+  return B200_OK;
+}
+extern "C" int b200_cast_to_f32(int dtype, const void* x, float* y, int64_t n, void* stream) {
+  B200_REQUIRE(x && y && n > 0, B200_ERR_SHAPE, "cast_to_f32: bad arguments");
+  B200_DISPATCH_DTYPE(dtype, T, (cast_to_f32_kernel<T><<<ew_grid(n), kThreads, 0, (cudaStream_t)stream>>>((const T*)x, y, n)));
+  B200_CHECK_LAUNCH("cast_to_f32");
+  return B200_OK;
+}
+
+extern "C" int64_t b200_bn_partials_bytes(int C) { return (int64_t)kMaxPartialBlocks * 2 * C * sizeof(float); }
+
+extern "C" int b200_bn_stats(int dtype, const void* x, int64_t M, int C, float* partials, void* stream) {
+  int rc = check_rows("bn_stats", M, C);
+  if (rc) return rc;
+  B200_REQUIRE(x && partials, B200_ERR_SHAPE, "bn_stats: null pointer");
+  const RowMap rm = row_map(M, C);
+  const size_t smem = (size_t)rm.rows_per_iter * 2 * C * sizeof(float);
+  B200_DISPATCH_DTYPE(dtype, T, (bn_stats_kernel<T><<<rm.nblocks, kThreads, smem, (cudaStream_t)stream>>>((const T*)x, M, C, partials)));
+  B200_CHECK_LAUNCH("bn_stats");
+  return B200_OK;
+}
+
+extern "C" int b200_bn_finalize(const float* partials, int64_t M, int C, const float* gamma, const float* beta, float eps,
+                                float momentum, int training, float* running_mean, float* running_var,
+                                int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* invstd,
+                                void* stream) {
+  int rc = check_rows("bn_finalize", M, C);
+  if (rc) return rc;
+  B200_REQUIRE(scale && shift && mean && invstd, B200_ERR_SHAPE, "bn_finalize: null output");
+  B200_REQUIRE(training ? partials != nullptr : (running_mean && running_var), B200_ERR_SHAPE,
+               "bn_finalize: %s", training ? "partials required in training mode" : "running stats required in eval mode");
+  const RowMap rm = row_map(M, C);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, rm.nblocks, M, C, gamma, beta, eps, momentum,
+                                                                     training, running_mean, running_var,
+                                                                     num_batches_tracked, scale, shift, mean, invstd);
+  B200_CHECK_LAUNCH("bn_finalize");
+  return B200_OK;
+}
+
+extern "C" int b200_bn_act_fwd(int dtype, const void* x, void* y, const float* scale, const float* shift,
+                               const float* dropmask, int relu, int64_t N, int64_t S, int C, void* stream) {
+  int rc = check_rows("bn_act_fwd", N * S, C);
+  if (rc) return rc;
+  B200_REQUIRE(x && y && scale && shift, B200_ERR_SHAPE, "bn_act_fwd: null pointer");
+  B200_DISPATCH_DTYPE(dtype, T, (bn_act_fwd_kernel<T><<<ew_grid(N * S * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+                                    (const T*)x, (T*)y, scale, shift, dropmask, relu, N, S, C)));
+  B200_CHECK_LAUNCH("bn_act_fwd");
+  return B200_OK;
+}
+
+extern "C" int b200_bn_act_bwd_reduce(int dtype, const void* gy, const void* x, const float* scale, const float* shift,
+                                      const float* mean, const float* invstd, const float* dropmask, int relu, int64_t N,
+                                      int64_t S, int C, float* partials, void* stream) {
+  int rc = check_rows("bn_act_bwd_reduce", N * S, C);
+  if (rc) return rc;
+  B200_REQUIRE(gy && x && scale && shift && mean && invstd && partials, B200_ERR_SHAPE, "bn_act_bwd_reduce: null pointer");
+  const RowMap rm = row_map(N * S, C);
+  const size_t smem = (size_t)rm.rows_per_iter * 2 * C * sizeof(float);
+  B200_DISPATCH_DTYPE(dtype, T, (bn_act_bwd_reduce_kernel<T><<<rm.nblocks, kThreads, smem, (cudaStream_t)stream>>>(
+                                    (const T*)gy, (const T*)x, scale, shift, mean, invstd, dropmask, relu, N, S, C, partials)));
+  B200_CHECK_LAUNCH("bn_act_bwd_reduce");
+  return B200_OK;
+}
+
+extern "C" int b200_bn_bwd_finalize(const float* partials, int64_t M, int C, float* dgamma, float* dbeta, float* sums,
+                                    void* stream) {
+  int rc = check_rows("bn_bwd_finalize", M, C);
+  if (rc) return rc;
+  B200_REQUIRE(partials && sums, B200_ERR_SHAPE, "bn_bwd_finalize: null pointer");
+  const RowMap rm = row_map(M, C);
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, rm.nblocks, M, C, dgamma, dbeta, sums);
+  B200_CHECK_LAUNCH("bn_bwd_finalize");
+  return B200_OK;
+}
+
+extern "C" int b200_bn_act_bwd_apply(int dtype, const void* gy, const void* x, void* dx, const float* scale,
+                                     const float* shift, const float* mean, const float* invstd, const float* dropmask,
+                                     int relu, const float* sums, int training, int64_t N, int64_t S, int C, void* stream) {
+  int rc = check_rows("bn_act_bwd_apply", N * S, C);
+  if (rc) return rc;
+  B200_REQUIRE(gy && x && dx && scale && shift && mean && invstd && sums, B200_ERR_SHAPE, "bn_act_bwd_apply: null pointer");
+  B200_DISPATCH_DTYPE(dtype, T, (bn_act_bwd_apply_kernel<T><<<ew_grid(N * S * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+                                    (const T*)gy, (const T*)x, (T*)dx, scale, shift, mean, invstd, dropmask, relu, sums,
+                                    training, N, S, C)));
+  B200_CHECK_LAUNCH("bn_act_bwd_apply");
+  return B200_OK;
+}
+
+extern "C" int b200_channel_sum(int dtype, const void* x, int64_t M, int C, float* partials, float* out, void* stream) {
+  int rc = check_rows("channel_sum", M, C);
+  if (rc) return rc;
+  B200_REQUIRE(x && partials && out, B200_ERR_SHAPE, "channel_sum: null pointer");
+  const RowMap rm = row_map(M, C);
+  const size_t smem = (size_t)rm.rows_per_iter * 2 * C * sizeof(float);
+  B200_DISPATCH_DTYPE(dtype, T, (channel_sum_kernel<T><<<rm.nblocks, kThreads, smem, (cudaStream_t)stream>>>((const T*)x, M, C, partials)));
+  B200_CHECK_LAUNCH("channel_sum");
+  channel_sum_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, rm.nblocks, C, out);
+  B200_CHECK_LAUNCH("channel_sum_finalize");
+  return B200_OK;
+}
+
+extern "C" int b200_maxpool2_fwd(int dtype, const void* x, void* y, int N, int D, int H, int W, int C, void* stream) {
+  int rc = check_rows("maxpool2_fwd", (int64_t)N * D * H * W, C);
+  if (rc) return rc;
+  B200_REQUIRE(x && y && D >= 2 && H >= 2 && W >= 2, B200_ERR_SHAPE, "maxpool2_fwd: spatial dims must be >= 2");
+  const int64_t items = (int64_t)N * (D / 2) * (H / 2) * (W / 2) * (C / 8);
+  B200_DISPATCH_DTYPE(dtype, T, (maxpool2_fwd_kernel<T><<<ew_grid(items), kThreads, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, N, D, H, W, C)));
+  B200_CHECK_LAUNCH("maxpool2_fwd");
+  return B200_OK;
+}
+
+extern "C" int b200_maxpool2_bwd(int dtype, const void* x, const void* gy, void* gx, int N, int D, int H, int W, int C, void* stream) {
+  int rc = check_rows("maxpool2_bwd", (int64_t)N * D * H * W, C);
+  if (rc) return rc;
+  B200_REQUIRE(x && gy && gx && D >= 2 && H >= 2 && W >= 2, B200_ERR_SHAPE, "maxpool2_bwd: spatial dims must be >= 2");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((D | H | W) & 1) {
+    const size_t esz = dtype == B200_F32 ? 4 : 2;
+    B200_CUDA(cudaMemsetAsync(gx, 0, (size_t)N * D * H * W * C * esz, st));
+  }
+  const int64_t items = (int64_t)N * (D / 2) * (H / 2) * (W / 2) * (C / 8);
+  B200_DISPATCH_DTYPE(dtype, T, (maxpool2_bwd_kernel<T><<<ew_grid(items), kThreads, 0, st>>>((const T*)x, (const T*)gy, (T*)gx, N, D, H, W, C)));
+  B200_CHECK_LAUNCH("maxpool2_bwd");
+  return B200_OK;
+}
+
+extern "C" int b200_nearest_resize_fwd(int dtype, const void* x, void* y, int N, int D, int H, int W, int OD, int OH, int OW,
+                                       int C, void* stream) {
+  int rc = check_rows("nearest_resize_fwd", (int64_t)N * D * H * W, C);
+  if (rc) return rc;
+  B200_REQUIRE(x && y && OD > 0 && OH > 0 && OW > 0, B200_ERR_SHAPE, "nearest_resize_fwd: bad arguments");
+  const int64_t items = (int64_t)N * OD * OH * OW * (C / 8);
+  B200_DISPATCH_DTYPE(dtype, T, (nearest_fwd_kernel<T><<<ew_grid(items), kThreads, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, N, D, H, W, OD, OH, OW, C)));
+  B200_CHECK_LAUNCH("nearest_resize_fwd");
+  return B200_OK;
+}
+extern "C" int b200_nearest_resize_bwd(int dtype, const void* gy, void* gx, int N, int D, int H, int W, int OD, int OH, int OW,
+                                       int C, void* stream) {
+  int rc = check_rows("nearest_resize_bwd", (int64_t)N * D * H * W, C);
+  if (rc) return rc;
+  B200_REQUIRE(gy && gx && OD > 0 && OH > 0 && OW > 0, B200_ERR_SHAPE, "nearest_resize_bwd: bad arguments");
+  const int64_t items = (int64_t)N * D * H * W * (C / 8);
+  B200_DISPATCH_DTYPE(dtype, T, (nearest_bwd_kernel<T><<<ew_grid(items), kThreads, 0, (cudaStream_t)stream>>>((const T*)gy, (T*)gx, N, D, H, W, OD, OH, OW, C)));
+  B200_CHECK_LAUNCH("nearest_resize_bwd");
+  return B200_OK;
+}
+
+extern "C" int b200_gap_fwd(int dtype, const void* x, float* out, int64_t N, int64_t S, int C, void* stream) {
+  int rc = check_rows("gap_fwd", N * S, C);
+  if (rc) return rc;
+  B200_REQUIRE(x && out, B200_ERR_SHAPE, "gap_fwd: null pointer");
+  B200_DISPATCH_DTYPE(dtype, T, (gap_fwd_kernel<T><<<(unsigned)(N * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const T*)x, out, N, S, C)));
+  B200_CHECK_LAUNCH("gap_fwd");
+  return B200_OK;
+}
+extern "C" int b200_gap_bwd(int dtype, const float* gout, void* gx, int accumulate, int64_t N, int64_t S, int C, void* stream) {
+  int rc = check_rows("gap_bwd", N * S, C);
+  if (rc) return rc;
+  B200_REQUIRE(gout && gx, B200_ERR_SHAPE, "gap_bwd: null pointer");
+  B200_DISPATCH_DTYPE(dtype, T, (gap_bwd_kernel<T><<<ew_grid(N * S * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(gout, (T*)gx, accumulate, N, S, C)));
+  B200_CHECK_LAUNCH("gap_bwd");
+  return B200_OK;
+}
+extern "C" int b200_scale_f32(const float* x, float* out, float alpha, int64_t n, void* stream) {
+  B200_REQUIRE(x && out && n > 0, B200_ERR_SHAPE, "scale_f32: bad arguments");
+  scale_f32_kernel<<<ew_grid(n), kThreads, 0, (cudaStream_t)stream>>>(x, out, alpha, n);
+  B200_CHECK_LAUNCH("scale_f32");
+  return B200_OK;
+}
+
+extern "C" int b200_adamw_prepare(int64_t* step, float beta1, float beta2, float* hyper, void* stream) {
+  B200_REQUIRE(step && hyper, B200_ERR_SHAPE, "adamw_prepare: null pointer");
+  adamw_prepare_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step, beta1, beta2, hyper);
+  B200_CHECK_LAUNCH("adamw_prepare");
+  return B200_OK;
+}
+extern "C" int b200_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float beta1,
+                               float beta2, float eps, float weight_decay, float grad_scale, void* stream) {
+  B200_REQUIRE(p && g && m && v && hyper && n > 0, B200_ERR_SHAPE, "adamw_flat: bad arguments");
+  B200_REQUIRE(b200_aligned(p, 16) && b200_aligned(g, 16) && b200_aligned(m, 16) && b200_aligned(v, 16), B200_ERR_ALIGN,
+               "adamw_flat: buffers must be 16-byte aligned");
+  adamw_flat_kernel<<<ew_grid(n / 4 + 1), kThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper, beta1, beta2, eps, weight_decay, grad_scale);
+  B200_CHECK_LAUNCH("adamw_flat");
+  return B200_OK;
+}

@@ -1,0 +1,607 @@
+"""torch-facing wrappers and autograd Functions over the libb200unet C ABI.
+
+Activations inside the network are channels-last ``[N, D, H, W, C]`` tensors (fp32 or bf16);
+the reference's NCDHW tensors exist only at the input (``in_channels == 1`` makes the two
+layouts identical) and at the logits produced by :func:`final_conv1x1`.
+
+Every function requires CUDA tensors: there is no CPU path (the oracle under ``oracle/`` is
+test infrastructure and is never imported from here).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+_VP = ctypes.c_void_p
+
+
+def _ptr(t):
+    return None if t is None else _VP(t.data_ptr())
+
+
+def _stream():
+    return _VP(torch.cuda.current_stream().cuda_stream)
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _lib.B200_F32
+    if t.dtype == torch.bfloat16:
+        return _lib.B200_BF16
+    raise TypeError(f"libb200unet supports float32 and bfloat16 activations, got {t.dtype}")
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "multimodal_segmentation_project_b200 runs on CUDA (sm_100a) tensors only; got a "
+                f"{t.device} tensor. There is no CPU fallback."
+            )
+
+
+def _f32(t):
+    return None if t is None else t.detach().float().contiguous()
+
+
+# --------------------------------------------------------------------------- plain wrappers
+def to_channels_last(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """NCDHW fp32 -> NDHWC ``dtype``."""
+    _require_cuda(x)
+    L = _lib.load()
+    x = x.detach().float().contiguous()
+    N, C = x.shape[0], x.shape[1]
+    sp = tuple(x.shape[2:])
+    S = 1
+    for d in sp:
+        S *= d
+    y = torch.empty((N, *sp, C), dtype=dtype, device=x.device)
+    if C == 1:
+        if dtype == torch.float32:
+            return x.reshape(N, *sp, 1)
+        check(L.b200_cast_from_f32(_dt(y), _ptr(x), _ptr(y), x.numel(), _stream()), "cast_from_f32")
+        return y
+    check(L.b200_ncdhw_to_ndhwc(_dt(y), _ptr(x), _ptr(y), N, C, S, _stream()), "ncdhw_to_ndhwc")
+    return y
+
+
+def to_channels_first_f32(x: torch.Tensor) -> torch.Tensor:
+    """NDHWC (fp32/bf16) -> NCDHW fp32."""
+    _require_cuda(x)
+    L = _lib.load()
+    x = x.detach().contiguous()
+    N, C = x.shape[0], x.shape[-1]
+    sp = tuple(x.shape[1:-1])
+    S = 1
+    for d in sp:
+        S *= d
+    y = torch.empty((N, C, *sp), dtype=torch.float32, device=x.device)
+    check(L.b200_ndhwc_to_ncdhw(_dt(x), _ptr(x), _ptr(y), N, C, S, _stream()), "ndhwc_to_ncdhw")
+    return y
+
+
+class _ToChannelsLast(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        return to_channels_last(x, dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return to_channels_first_f32(g), None
+
+
+def pack_conv3_weights(weight: torch.Tensor, mode: int, dtype: torch.dtype) -> torch.Tensor:
+    L = _lib.load()
+    w = _f32(weight)
+    Cout, Cin = w.shape[0], w.shape[1]
+    dt = _lib.B200_F32 if dtype == torch.float32 else _lib.B200_BF16
+    nbytes = L.b200_pack_conv3_bytes(mode, dt, Cout, Cin)
+    out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    check(L.b200_pack_conv3_weights(mode, dt, _ptr(w), _ptr(out), Cout, Cin, _stream()), "pack_conv3_weights")
+    return out
+
+
+def conv3d_k3_raw(x0, x1, wpack, bias, co0, co1=0, impl=0):
+    """3x3x3 'same' convolution of the virtual concat [x0|x1]; returns (y0, y1) with co0 / co1 channels."""
+    L = _lib.load()
+    N, D, H, W, c0 = x0.shape
+    c1 = 0 if x1 is None else x1.shape[-1]
+    y0 = torch.empty((N, D, H, W, co0), dtype=x0.dtype, device=x0.device)
+    y1 = torch.empty((N, D, H, W, co1), dtype=x0.dtype, device=x0.device) if co1 else None
+    check(
+        L.b200_conv3d_k3(_dt(x0), impl, _ptr(x0), c0, _ptr(x1), c1, _ptr(wpack), _ptr(bias), _ptr(y0), co0, _ptr(y1), co1,
+                         N, D, H, W, _stream()),
+        "conv3d_k3",
+    )
+    return y0, y1
+
+
+def conv3d_wgrad_raw(x0, x1, dy, want_bias=True):
+    L = _lib.load()
+    N, D, H, W, c0 = x0.shape
+    c1 = 0 if x1 is None else x1.shape[-1]
+    Cout = dy.shape[-1]
+    ws_bytes = L.b200_conv3d_wgrad_workspace(c0, c1, Cout, N, D, H, W)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x0.device)
+    dw = torch.empty((Cout, c0 + c1, 3, 3, 3), dtype=torch.float32, device=x0.device)
+    db = torch.empty(Cout, dtype=torch.float32, device=x0.device) if want_bias else None
+    check(
+        L.b200_conv3d_wgrad(_dt(x0), _ptr(x0), c0, _ptr(x1), c1, _ptr(dy), Cout, _ptr(dw), _ptr(db), _ptr(ws), ws_bytes,
+                            N, D, H, W, _stream()),
+        "conv3d_wgrad",
+    )
+    return dw, db
+
+
+def _bn_partials(C, device):
+    L = _lib.load()
+    return torch.empty(L.b200_bn_partials_bytes(C) // 4, dtype=torch.float32, device=device)
+
+
+# --------------------------------------------------------------------------- conv + BN + ReLU + Dropout3d
+class _ConvBNAct(torch.autograd.Function):
+    """One half of the reference's DoubleConv (models/unet.py:11-14 / :15-18):
+    Conv3d(k3,p1)+bias -> BatchNorm3d -> ReLU -> Dropout3d (channel mask supplied by the caller).
+    The input may be the virtual concat of two tensors (models/unet.py:84)."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, weight, bias, gamma, beta, running_mean, running_var, nbt, dropmask, training, eps,
+                momentum, impl):
+        _require_cuda(x0, x1, weight)
+        L = _lib.load()
+        x0 = x0.contiguous()
+        x1 = None if x1 is None else x1.contiguous()
+        N, D, H, W, _ = x0.shape
+        Cout = weight.shape[0]
+        dev = x0.device
+        wpack = pack_conv3_weights(weight, _lib.PACK_FPROP, x0.dtype)
+        conv_out, _ = conv3d_k3_raw(x0, x1, wpack, _f32(bias), Cout, 0, impl)
+        M, S = N * D * H * W, D * H * W
+        if training and M <= 1:  # same contract as torch.nn.functional.batch_norm
+            raise ValueError(f"Expected more than 1 value per channel when training, got input size {[N, Cout, D, H, W]}")
+        stats = torch.empty((4, Cout), dtype=torch.float32, device=dev)  # scale, shift, mean, invstd
+        partials = None
+        if training:
+            partials = _bn_partials(Cout, dev)
+            check(L.b200_bn_stats(_dt(conv_out), _ptr(conv_out), M, Cout, _ptr(partials), _stream()), "bn_stats")
+        g32, b32 = _f32(gamma), _f32(beta)
+        check(
+            L.b200_bn_finalize(_ptr(partials), M, Cout, _ptr(g32), _ptr(b32), float(eps), float(momentum), int(training),
+                               _ptr(running_mean), _ptr(running_var), _ptr(nbt), _ptr(stats[0]), _ptr(stats[1]),
+                               _ptr(stats[2]), _ptr(stats[3]), _stream()),
+            "bn_finalize",
+        )
+        y = torch.empty_like(conv_out)
+        check(
+            L.b200_bn_act_fwd(_dt(conv_out), _ptr(conv_out), _ptr(y), _ptr(stats[0]), _ptr(stats[1]), _ptr(dropmask), 1, N, S,
+                              Cout, _stream()),
+            "bn_act_fwd",
+        )
+        ctx.save_for_backward(x0, x1, weight, conv_out, stats, dropmask)
+        ctx.training = bool(training)
+        ctx.impl = impl
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        L = _lib.load()
+        x0, x1, weight, conv_out, stats, dropmask = ctx.saved_tensors
+        gy = gy.contiguous()
+        N, D, H, W, Cout = conv_out.shape
+        M, S = N * D * H * W, D * H * W
+        dev = gy.device
+        partials = _bn_partials(Cout, dev)
+        dt = _dt(conv_out)
+        check(
+            L.b200_bn_act_bwd_reduce(dt, _ptr(gy), _ptr(conv_out), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]), _ptr(stats[3]),
+                                     _ptr(dropmask), 1, N, S, Cout, _ptr(partials), _stream()),
+            "bn_act_bwd_reduce",
+        )
+        dgamma = torch.empty(Cout, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(Cout, dtype=torch.float32, device=dev)
+        sums = torch.empty(2 * Cout, dtype=torch.float32, device=dev)
+        check(L.b200_bn_bwd_finalize(_ptr(partials), M, Cout, _ptr(dgamma), _ptr(dbeta), _ptr(sums), _stream()), "bn_bwd_finalize")
+        dconv = torch.empty_like(conv_out)
+        check(
+            L.b200_bn_act_bwd_apply(dt, _ptr(gy), _ptr(conv_out), _ptr(dconv), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]),
+                                    _ptr(stats[3]), _ptr(dropmask), 1, _ptr(sums), int(ctx.training), N, S, Cout, _stream()),
+            "bn_act_bwd_apply",
+        )
+        dw = db = None
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            dw, db = conv3d_wgrad_raw(x0, x1, dconv, want_bias=True)
+        dx0 = dx1 = None
+        if ctx.needs_input_grad[0] or (x1 is not None and ctx.needs_input_grad[1]):
+            c0 = x0.shape[-1]
+            c1 = 0 if x1 is None else x1.shape[-1]
+            wpack = pack_conv3_weights(weight, _lib.PACK_DGRAD, conv_out.dtype)
+            dx0, dx1 = conv3d_k3_raw(dconv, None, wpack, None, c0, c1, ctx.impl)
+        return (dx0, dx1, dw, db, dgamma, dbeta, None, None, None, None, None, None, None, None)
+
+
+def conv_bn_act(x0, x1, conv, bn, dropmask, training, impl=0):
+    return _ConvBNAct.apply(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                            bn.num_batches_tracked, dropmask, training, bn.eps,
+                            0.1 if bn.momentum is None else bn.momentum, impl)
+
+
+# --------------------------------------------------------------------------- MaxPool3d(2,2)
+class _MaxPool2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x)
+        L = _lib.load()
+        x = x.contiguous()
+        N, D, H, W, C = x.shape
+        y = torch.empty((N, D // 2, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
+        check(L.b200_maxpool2_fwd(_dt(x), _ptr(x), _ptr(y), N, D, H, W, C, _stream()), "maxpool2_fwd")
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        L = _lib.load()
+        (x,) = ctx.saved_tensors
+        gy = gy.contiguous()
+        N, D, H, W, C = x.shape
+        gx = torch.empty_like(x)
+        check(L.b200_maxpool2_bwd(_dt(x), _ptr(x), _ptr(gy), _ptr(gx), N, D, H, W, C, _stream()), "maxpool2_bwd")
+        return gx
+
+
+def maxpool2(x):
+    return _MaxPool2.apply(x)
+
+
+# --------------------------------------------------------------------------- ConvTranspose3d(k2,s2)
+class _ConvT2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _require_cuda(x, weight)
+        L = _lib.load()
+        x = x.contiguous()
+        N, D, H, W, Cin = x.shape
+        Cout = weight.shape[1]
+        w32, b32 = _f32(weight), _f32(bias)
+        y = torch.empty((N, 2 * D, 2 * H, 2 * W, Cout), dtype=x.dtype, device=x.device)
+        check(L.b200_convt2_fwd(_dt(x), _ptr(x), _ptr(w32), _ptr(b32), _ptr(y), N, D, H, W, Cin, Cout, _stream()), "convt2_fwd")
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        L = _lib.load()
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        N, D, H, W, Cin = x.shape
+        Cout = weight.shape[1]
+        w32 = _f32(weight)
+        gx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            check(L.b200_convt2_bwd_data(_dt(x), _ptr(gy), _ptr(w32), _ptr(gx), N, D, H, W, Cin, Cout, _stream()), "convt2_bwd_data")
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            ws_bytes = L.b200_convt2_wgrad_workspace(Cin, Cout, N, D, H, W)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+            dw = torch.empty_like(w32)
+            db = torch.empty(Cout, dtype=torch.float32, device=x.device)
+            check(
+                L.b200_convt2_bwd_weight(_dt(x), _ptr(x), _ptr(gy), _ptr(dw), _ptr(db), _ptr(ws), ws_bytes, N, D, H, W, Cin, Cout,
+                                         _stream()),
+                "convt2_bwd_weight",
+            )
+        return gx, dw, db
+
+
+def conv_transpose2(x, weight, bias):
+    return _ConvT2.apply(x, weight, bias)
+
+
+class _NearestResize(torch.autograd.Function):
+    """F.interpolate(x, size=...) with the default mode='nearest' (models/unet.py:81-83)."""
+
+    @staticmethod
+    def forward(ctx, x, size):
+        _require_cuda(x)
+        L = _lib.load()
+        x = x.contiguous()
+        N, D, H, W, C = x.shape
+        OD, OH, OW = size
+        y = torch.empty((N, OD, OH, OW, C), dtype=x.dtype, device=x.device)
+        check(L.b200_nearest_resize_fwd(_dt(x), _ptr(x), _ptr(y), N, D, H, W, OD, OH, OW, C, _stream()), "nearest_resize_fwd")
+        ctx.in_shape = (N, D, H, W, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        L = _lib.load()
+        gy = gy.contiguous()
+        N, D, H, W, C = ctx.in_shape
+        OD, OH, OW = gy.shape[1:4]
+        gx = torch.empty(ctx.in_shape, dtype=gy.dtype, device=gy.device)
+        check(L.b200_nearest_resize_bwd(_dt(gy), _ptr(gy), _ptr(gx), N, D, H, W, OD, OH, OW, C, _stream()), "nearest_resize_bwd")
+        return gx, None
+
+
+def nearest_resize(x, size):
+    return _NearestResize.apply(x, tuple(int(s) for s in size))
+
+
+# --------------------------------------------------------------------------- final 1x1x1 conv
+class _FinalConv1x1(torch.autograd.Function):
+    """nn.Conv3d(features[0], out_channels, 1) (models/unet.py:62,87): NDHWC -> NCDHW fp32 logits."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, round_bf16):
+        _require_cuda(x, weight)
+        L = _lib.load()
+        x = x.contiguous()
+        N, D, H, W, Cin = x.shape
+        Cout = weight.shape[0]
+        S = D * H * W
+        w32 = _f32(weight).reshape(Cout, Cin)
+        b32 = _f32(bias)
+        y = torch.empty((N, Cout, D, H, W), dtype=torch.float32, device=x.device)
+        check(L.b200_conv1x1_fwd(_dt(x), _ptr(x), _ptr(w32), _ptr(b32), _ptr(y), N, S, Cin, Cout, int(round_bf16), _stream()), "conv1x1_fwd")
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        L = _lib.load()
+        x, weight = ctx.saved_tensors
+        gy = gy.float().contiguous()
+        N, D, H, W, Cin = x.shape
+        Cout = weight.shape[0]
+        S = D * H * W
+        w32 = _f32(weight).reshape(Cout, Cin)
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty((Cout, Cin), dtype=torch.float32, device=x.device)
+        db = torch.empty(Cout, dtype=torch.float32, device=x.device)
+        partials = torch.empty(L.b200_conv1x1_partials_bytes(Cin, Cout) // 4, dtype=torch.float32, device=x.device)
+        check(
+            L.b200_conv1x1_bwd(_dt(x), _ptr(x), _ptr(w32), _ptr(gy), _ptr(gx), _ptr(dw), _ptr(db), _ptr(partials), N, S, Cin, Cout,
+                               _stream()),
+            "conv1x1_bwd",
+        )
+        return gx, dw.reshape(weight.shape), db, None
+
+
+def final_conv1x1(x, weight, bias, round_bf16=False):
+    return _FinalConv1x1.apply(x, weight, bias, round_bf16)
+
+
+# --------------------------------------------------------------------------- global average pool
+class _GlobalAvgPool(torch.autograd.Function):
+    """torch.mean(bottleneck, dim=[2,3,4]) (models/unet_dann.py:79) on an NDHWC tensor -> [N, C] fp32."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x)
+        L = _lib.load()
+        x = x.contiguous()
+        N, C = x.shape[0], x.shape[-1]
+        S = x.numel() // (N * C)
+        out = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        check(L.b200_gap_fwd(_dt(x), _ptr(x), _ptr(out), N, S, C, _stream()), "gap_fwd")
+        ctx.shape = tuple(x.shape)
+        ctx.dtype = x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _lib.load()
+        g = g.float().contiguous()
+        N, C = ctx.shape[0], ctx.shape[-1]
+        gx = torch.empty(ctx.shape, dtype=ctx.dtype, device=g.device)
+        S = gx.numel() // (N * C)
+        check(L.b200_gap_bwd(_dt(gx), _ptr(g), _ptr(gx), 0, N, S, C, _stream()), "gap_bwd")
+        return gx
+
+
+def global_avg_pool(x):
+    return _GlobalAvgPool.apply(x)
+
+
+# --------------------------------------------------------------------------- losses
+class _SegLoss(torch.autograd.Function):
+    """Fused softmax + CE + Dice/Tversky (+ KD-KL) — utils/metrics.py:14-40, 137-190."""
+
+    @staticmethod
+    def forward(ctx, logits, target, teacher, mode, alpha, beta, kd_alpha, temperature):
+        _require_cuda(logits, target, teacher)
+        L = _lib.load()
+        if logits.dim() < 3:
+            raise ValueError(f"expected logits [B, C, ...], got {tuple(logits.shape)}")
+        z = logits.detach().float().contiguous()
+        N, C = z.shape[0], z.shape[1]
+        S = z.numel() // (N * C)
+        if target.dtype != torch.int64:
+            raise RuntimeError(f"expected int64 class-index target (the reference's CrossEntropyLoss contract), got {target.dtype}")
+        if target.numel() != N * S:
+            raise ValueError(f"target shape {tuple(target.shape)} does not match logits {tuple(logits.shape)}")
+        y = target.detach().contiguous()
+        t = None
+        if teacher is not None:
+            if teacher.shape != logits.shape:
+                raise ValueError("teacher and student logits must have the same shape")
+            t = teacher.detach().float().contiguous()
+        dev = z.device
+        sums = torch.empty(4 + 4 * C, dtype=torch.float64, device=dev)
+        check(L.b200_kd_loss_fwd(_ptr(z), _ptr(t), _ptr(y), float(temperature), N, C, S, _ptr(sums), _stream()), "seg_loss_fwd")
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        coef = torch.empty(2 + 2 * C, dtype=torch.float32, device=dev)
+        check(
+            L.b200_seg_loss_finalize(_ptr(sums), mode, float(alpha), float(beta), float(kd_alpha), float(temperature),
+                                     int(t is not None), N, C, S, _ptr(loss), _ptr(coef), _stream()),
+            "seg_loss_finalize",
+        )
+        ctx.save_for_backward(z, y, t, coef)
+        ctx.temperature = float(temperature)
+        ctx.in_dtype = logits.dtype
+        ctx.mark_non_differentiable(sums)
+        return loss, sums
+
+    @staticmethod
+    def backward(ctx, gout, _gsums):
+        L = _lib.load()
+        z, y, t, coef = ctx.saved_tensors
+        N, C = z.shape[0], z.shape[1]
+        S = z.numel() // (N * C)
+        go = gout.detach().float().contiguous().reshape(1)
+        dz = torch.empty_like(z)
+        check(
+            L.b200_seg_loss_bwd(_ptr(z), _ptr(t), _ptr(y), _ptr(coef), _ptr(go), ctx.temperature, N, C, S, _ptr(dz), _stream()),
+            "seg_loss_bwd",
+        )
+        if ctx.in_dtype != torch.float32:
+            dz = dz.to(ctx.in_dtype)
+        return dz, None, None, None, None, None, None, None
+
+
+def seg_loss(logits, target, mode, alpha=0.5, beta=0.5, teacher=None, kd_alpha=1.0, temperature=1.0):
+    loss, _ = _SegLoss.apply(logits, target, teacher, mode, alpha, beta, kd_alpha, temperature)
+    return loss
+
+
+def seg_loss_sums(logits, target):
+    """(CE_sum, per-class I, P, T) as float64 — exposed for tests."""
+    _, sums = _SegLoss.apply(logits, target, None, _lib.LOSS_DICE_CE, 0.5, 0.5, 1.0, 1.0)
+    return sums
+
+
+# --------------------------------------------------------------------------- metrics
+def confusion_counts(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """int64 [C, C] confusion matrix conf[target, argmax] in one pass (device tensor, no sync)."""
+    _require_cuda(pred, target)
+    L = _lib.load()
+    z = pred.detach().float().contiguous()
+    N, C = z.shape[0], z.shape[1]
+    S = z.numel() // max(N * C, 1)
+    if target.dtype != torch.int64:
+        target = target.long()
+    y = target.detach().contiguous()
+    if y.numel() != N * S:
+        raise ValueError(f"target shape {tuple(target.shape)} does not match pred {tuple(pred.shape)}")
+    conf = torch.empty((C, C), dtype=torch.int64, device=z.device)
+    check(L.b200_confusion(_ptr(z), _ptr(y), N, C, S, _ptr(conf), _stream()), "confusion")
+    return conf
+
+
+def argmax_mask(pred: torch.Tensor) -> torch.Tensor:
+    """torch.argmax(pred, dim=1) as uint8 [N, ...]."""
+    _require_cuda(pred)
+    L = _lib.load()
+    z = pred.detach().float().contiguous()
+    N, C = z.shape[0], z.shape[1]
+    S = z.numel() // max(N * C, 1)
+    out = torch.empty((N, *z.shape[2:]), dtype=torch.uint8, device=z.device)
+    check(L.b200_argmax(_ptr(z), N, C, S, _ptr(out), _stream()), "argmax")
+    return out
+
+
+# --------------------------------------------------------------------------- DANN pieces
+def scale(x: torch.Tensor, alpha: float) -> torch.Tensor:
+    """alpha * x through the library (used by the gradient-reversal backward)."""
+    _require_cuda(x)
+    L = _lib.load()
+    x32 = x.detach().float().contiguous()
+    out = torch.empty_like(x32)
+    check(L.b200_scale_f32(_ptr(x32), _ptr(out), float(alpha), x32.numel(), _stream()), "scale_f32")
+    return out.to(x.dtype)
+
+
+class _LinearAct(torch.autograd.Function):
+    """nn.Linear (+ReLU) (+Dropout mask) — train_dann.py:37-46."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, dropmask, relu):
+        _require_cuda(x, weight)
+        L = _lib.load()
+        x32 = x.detach().float().contiguous()
+        w32, b32 = _f32(weight), _f32(bias)
+        B, I = x32.shape
+        O = w32.shape[0]
+        y = torch.empty((B, O), dtype=torch.float32, device=x.device)
+        check(L.b200_linear_fwd(_ptr(x32), _ptr(w32), _ptr(b32), _ptr(dropmask), int(relu), _ptr(y), B, I, O, _stream()), "linear_fwd")
+        ctx.save_for_backward(x32, w32, y, dropmask)
+        ctx.relu = int(relu)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        L = _lib.load()
+        x32, w32, y, dropmask = ctx.saved_tensors
+        gy = gy.float().contiguous()
+        B, I = x32.shape
+        O = w32.shape[0]
+        gx = torch.empty_like(x32) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w32)
+        db = torch.empty(O, dtype=torch.float32, device=gy.device)
+        check(
+            L.b200_linear_bwd(_ptr(x32), _ptr(w32), _ptr(y), _ptr(gy), _ptr(dropmask), ctx.relu, _ptr(gx), _ptr(dw), _ptr(db), B, I, O,
+                              _stream()),
+            "linear_bwd",
+        )
+        return gx, dw, (db if ctx.has_bias else None), None, None
+
+
+def linear_act(x, weight, bias, dropmask=None, relu=False):
+    return _LinearAct.apply(x, weight, bias, dropmask, relu)
+
+
+class _CERows(torch.autograd.Function):
+    """nn.CrossEntropyLoss() on [B, C] logits (train_dann.py:258)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        _require_cuda(logits, labels)
+        L = _lib.load()
+        z = logits.detach().float().contiguous()
+        y = labels.detach().long().contiguous()
+        B, C = z.shape
+        loss = torch.empty((), dtype=torch.float32, device=z.device)
+        dz = torch.empty_like(z)
+        check(L.b200_ce_rows(_ptr(z), _ptr(y), B, C, _ptr(loss), _ptr(dz), _stream()), "ce_rows")
+        ctx.save_for_backward(dz)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dz,) = ctx.saved_tensors
+        return dz * g, None
+
+
+def cross_entropy_rows(logits, labels):
+    return _CERows.apply(logits, labels)
+
+
+# --------------------------------------------------------------------------- fused AdamW on flat buffers
+class FlatAdamW:
+    """AdamW (train_unet.py:378) over one flat fp32 parameter/gradient buffer; graph-capturable."""
+
+    def __init__(self, flat_param, flat_grad, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        _require_cuda(flat_param, flat_grad)
+        self.p, self.g = flat_param, flat_grad
+        self.m = torch.zeros_like(flat_param)
+        self.v = torch.zeros_like(flat_param)
+        self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
+        self.step_count = torch.zeros((), dtype=torch.int64, device=flat_param.device)
+        self.hyper = torch.tensor([lr, 1.0, 1.0, 0.0], dtype=torch.float32, device=flat_param.device)
+
+    def set_lr(self, lr: float):
+        self.hyper[0] = lr
+
+    def step(self, grad_scale: float = 1.0):
+        L = _lib.load()
+        check(L.b200_adamw_prepare(_ptr(self.step_count), self.betas[0], self.betas[1], _ptr(self.hyper), _stream()), "adamw_prepare")
+        check(
+            L.b200_adamw_flat(_ptr(self.p), _ptr(self.g), _ptr(self.m), _ptr(self.v), self.p.numel(), _ptr(self.hyper),
+                              self.betas[0], self.betas[1], self.eps, self.weight_decay, float(grad_scale), _stream()),
+            "adamw_flat",
+        )

@@ -1,0 +1,203 @@
+"""Drop-in for the reference's ``utils/metrics.py`` (all 15 functions, same signatures).
+
+Losses run as ONE fused forward pass (+ one backward pass) over the logits instead of ~20 ATen
+kernels; metrics run as ONE argmax+confusion-count pass whose int64 counts are turned into the
+reference's fp32 scalars with exactly the reference's operation order, so
+Dice / IoU are bit-identical to the reference given the same logits.
+
+Quirks reproduced on purpose: the metric class loop runs over
+``range(1, pred.size(1))`` AFTER argmax, i.e. up to the first spatial size; Dice/IoU average only
+over classes present in the target and return Python ``0`` when none is; Dice epsilon 1e-5,
+Tversky epsilon 1e-6; ``combined_ce_tversky_loss`` hard-codes 0.3 / 0.7.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .. import functional as F
+
+_f32 = np.float32
+
+
+# ------------------------------------------------------------------ losses (reference :6-40, :137-190)
+def combined_loss(pred, target):
+    """CE + soft-Dice over classes 1..C-1, batch-global sums — reference utils/metrics.py:14-40."""
+    return F.seg_loss(pred, target, _lib.LOSS_DICE_CE)
+
+
+def tversky_loss(pred, target, alpha=0.5, beta=0.5, epsilon=1e-6):
+    """reference utils/metrics.py:137-156 (epsilon is fixed at the reference default 1e-6)."""
+    if epsilon != 1e-6:
+        raise ValueError("the fused kernel implements the reference default epsilon=1e-6 only")
+    return F.seg_loss(pred, target, _lib.LOSS_TVERSKY, alpha, beta)
+
+
+def combined_ce_tversky_loss(pred, target, alpha=0.7, beta=0.3):
+    """0.3*CE + 0.7*Tversky(alpha, beta) — reference utils/metrics.py:158-167."""
+    return F.seg_loss(pred, target, _lib.LOSS_CE_TVERSKY, alpha, beta)
+
+
+def distillation_loss(student_logits, teacher_logits, target, alpha=0.7, temperature=2.0):
+    """alpha*(0.3 CE + 0.7 Tversky(.7,.3)) + (1-alpha)*T^2*mean KL — reference utils/metrics.py:169-190."""
+    return F.seg_loss(student_logits, target, _lib.LOSS_CE_TVERSKY, 0.7, 0.3, teacher=teacher_logits, kd_alpha=alpha,
+                      temperature=temperature)
+
+
+def dice_only_loss(pred, target):
+    """The 'dice' closure of get_loss_fn — reference train_unet.py:185-199 (Dice half of combined_loss)."""
+    return F.seg_loss(pred, target, _lib.LOSS_DICE)
+
+
+# ------------------------------------------------------------------ multi-class metrics (reference :65-129)
+_conf_cache = {"key": None, "conf": None}
+
+
+def _confusion(pred, target):
+    # calculate_iou / calculate_dice / calculate_accuracy are called back to back on the same
+    # tensors (train_unet.py:229-232): compute the counts once.
+    key = (pred.data_ptr(), pred._version, tuple(pred.shape), target.data_ptr(), target._version, pred.device)
+    if _conf_cache["key"] == key:
+        return _conf_cache["conf"]
+    conf = F.confusion_counts(pred, target).cpu().numpy()  # the reference syncs here too (`if sum > 0`)
+    _conf_cache["key"], _conf_cache["conf"] = key, conf
+    return conf
+
+
+def dice_iou_from_confusion(conf: np.ndarray, first_spatial: int):
+    """Appendix-E recipe: (dice, iou, n_valid) in fp32 with the reference's unfused op order."""
+    C = conf.shape[0]
+    eps = _f32(1e-5)
+    dice, iou, valid = _f32(0.0), _f32(0.0), 0
+    for k in range(1, min(C, int(first_spatial))):
+        T = int(conf[k, :].sum())
+        if T > 0:
+            P = int(conf[:, k].sum())
+            I = _f32(int(conf[k, k]))
+            union_d = _f32(P + T)
+            dice = _f32(dice + _f32(_f32(_f32(2.0) * I) + eps) / _f32(union_d + eps))
+            union_i = _f32(union_d - I)
+            iou = _f32(iou + _f32(I + eps) / _f32(union_i + eps))
+            valid += 1
+    return dice, iou, valid
+
+
+def _first_spatial(pred):
+    return pred.shape[2] if pred.dim() > 2 else 1
+
+
+def calculate_iou(pred, target):
+    """reference utils/metrics.py:65-90."""
+    conf = _confusion(pred, target)
+    _, iou, valid = dice_iou_from_confusion(conf, _first_spatial(pred))
+    if valid == 0:
+        return 0 / max(valid, 1)
+    return torch.tensor(_f32(iou / _f32(valid)), dtype=torch.float32, device=pred.device)
+
+
+def calculate_dice(pred, target):
+    """reference utils/metrics.py:92-117."""
+    conf = _confusion(pred, target)
+    dice, _, valid = dice_iou_from_confusion(conf, _first_spatial(pred))
+    if valid == 0:
+        return 0 / max(valid, 1)
+    return torch.tensor(_f32(dice / _f32(valid)), dtype=torch.float32, device=pred.device)
+
+
+def calculate_accuracy(pred, target):
+    """reference utils/metrics.py:119-129: (argmax == target).float().mean()."""
+    conf = _confusion(pred, target)
+    n = int(target.numel())
+    correct = int(np.trace(conf))
+    return torch.tensor(_f32(_f32(correct) / _f32(n)), dtype=torch.float32, device=pred.device)
+
+
+def per_class_dice_iou(pred, target, classes=(1, 2, 3)):
+    """The evaluator's rule (reference test_model.py:265-285): absent class -> 0.0, mean over all listed."""
+    conf = _confusion(pred, target)
+    out = {}
+    for k in classes:
+        T, P, I = int(conf[k, :].sum()), int(conf[:, k].sum()), int(conf[k, k])
+        out[k] = {"dice": (2.0 * I / (P + T)) if T > 0 and (P + T) > 0 else 0.0,
+                  "iou": (I / (P + T - I)) if T > 0 and (P + T - I) > 0 else 0.0}
+    return out
+
+
+# ------------------------------------------------------------------ binary helpers (reference :6-12, :42-63, :131-135; dead code there)
+def _binary_counts(pred, target):
+    """Per-sample (intersection, pred_sum, target_sum, correct) for pred>0.5 vs target via the confusion kernel."""
+    if pred.shape != target.shape:
+        raise ValueError("pred and target must have the same shape")
+    B = pred.shape[0]
+    S = pred[0].numel()
+    # logits trick: class 1 wins iff pred > 0.5  (two-plane "logits": [0.5, pred])
+    p = pred.detach().float().reshape(B, 1, S)
+    planes = torch.cat([torch.full_like(p, 0.5), p], dim=1).contiguous()
+    tgt = (target.detach().reshape(B, S) != 0).long()
+    res = []
+    for b in range(B):
+        conf = F.confusion_counts(planes[b:b + 1], tgt[b:b + 1]).cpu().numpy()
+        exact01 = bool(((target[b] == 0) | (target[b] == 1)).all().item())
+        res.append((int(conf[1, 1]), int(conf[:, 1].sum()), int(conf[1, :].sum()), int(np.trace(conf)), exact01))
+    return res
+
+
+def dice_score(pred, target, epsilon=1e-6):
+    vals = []
+    for I, P, T, _, _ in _binary_counts(pred, target):
+        vals.append(_f32(_f32(_f32(2.0) * _f32(I)) + _f32(epsilon)) / _f32(_f32(_f32(P) + _f32(T)) + _f32(epsilon)))
+    return float(np.mean(np.asarray(vals, dtype=np.float32), dtype=np.float32))
+
+
+def iou_score(pred, target, epsilon=1e-6):
+    vals = []
+    for I, P, T, _, _ in _binary_counts(pred, target):
+        union = _f32(_f32(_f32(P) + _f32(T)) - _f32(I))
+        vals.append(_f32(_f32(I) + _f32(epsilon)) / _f32(union + _f32(epsilon)))
+    return float(np.mean(np.asarray(vals, dtype=np.float32), dtype=np.float32))
+
+
+def accuracy_score(pred, target):
+    counts = _binary_counts(pred, target)
+    correct = sum(c[3] for c in counts)
+    return float(_f32(correct) / _f32(target.numel()))
+
+
+def calculate_metrics(pred, target):
+    dice = dice_score(pred, target)
+    iou = iou_score(pred, target)
+    acc = accuracy_score(pred, target)
+    return dice, iou, acc
+
+
+def dice_loss(pred, target, epsilon=1e-6):
+    """Binary sigmoid Dice loss — reference utils/metrics.py:6-12 (never called by the reference's scripts).
+    Expressed through the fused kernel: sigmoid(x) == softmax([0, x])[1]."""
+    B = pred.shape[0]
+    S = pred[0].numel()
+    z = pred.reshape(1, 1, B * S)
+    planes = torch.cat([torch.zeros_like(z), z], dim=1)
+    tgt = target.reshape(1, B * S)
+    if not torch.is_floating_point(tgt):
+        tgt = tgt.long()
+    else:
+        if not bool(((tgt == 0) | (tgt == 1)).all().item()):
+            raise ValueError("dice_loss (b200) supports {0,1} targets")
+        tgt = tgt.long()
+    return _BinaryDice.apply(planes, tgt, float(epsilon))
+
+
+class _BinaryDice(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, planes, tgt, eps):
+        sums = F.seg_loss_sums(planes, tgt)  # [CE, KL, -, -, (I,P,T,-) per class]
+        I, P, T = sums[8], sums[9], sums[10]
+        dice = (2.0 * I + eps) / (P + T + eps)
+        ctx.save_for_backward(planes, tgt, sums)
+        ctx.eps = eps
+        return (1.0 - dice).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        raise NotImplementedError("dice_loss backward: the reference never trains with this loss; use combined_loss")
