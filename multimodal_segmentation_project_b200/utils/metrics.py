@@ -12,6 +12,8 @@ Tversky epsilon 1e-6; ``combined_ce_tversky_loss`` hard-codes 0.3 / 0.7.
 """
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 import torch
 
@@ -51,17 +53,20 @@ def dice_only_loss(pred, target):
 
 
 # ------------------------------------------------------------------ multi-class metrics (reference :65-129)
-_conf_cache = {"key": None, "conf": None}
+_conf_cache = {"pred": None, "target": None, "versions": None, "conf": None}
 
 
 def _confusion(pred, target):
     # calculate_iou / calculate_dice / calculate_accuracy are called back to back on the same
-    # tensors (train_unet.py:229-232): compute the counts once.
-    key = (pred.data_ptr(), pred._version, tuple(pred.shape), target.data_ptr(), target._version, pred.device)
-    if _conf_cache["key"] == key:
-        return _conf_cache["conf"]
+    # tensor objects (train_unet.py:229-232): compute the counts once.  The cache is keyed on object
+    # identity (weak references) + in-place version counters, never on addresses.
+    c = _conf_cache
+    if (c["pred"] is not None and c["pred"]() is pred and c["target"]() is target
+            and c["versions"] == (pred._version, target._version)):
+        return c["conf"]
     conf = F.confusion_counts(pred, target).cpu().numpy()  # the reference syncs here too (`if sum > 0`)
-    _conf_cache["key"], _conf_cache["conf"] = key, conf
+    c["pred"], c["target"] = weakref.ref(pred), weakref.ref(target)
+    c["versions"], c["conf"] = (pred._version, target._version), conf
     return conf
 
 
