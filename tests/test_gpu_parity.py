@@ -559,3 +559,49 @@ def test_fused_adamw_matches_torch(cuda_dev):
         g.copy_(gr * 2.0)
         ours.step(grad_scale=0.5)
     assert rel_l2(p, ref) <= 1e-6
+
+
+# --------------------------------------------------------------------------------- tcgen05 convolution
+TC_CASES = [
+    # N, D, H, W, c0, c1, co0, co1
+    (1, 8, 16, 16, 16, 0, 16, 0),
+    (2, 5, 20, 24, 16, 0, 32, 0),
+    (1, 4, 8, 8, 32, 32, 32, 0),
+    (1, 9, 16, 32, 32, 0, 16, 16),     # data-gradient style split output
+    (1, 4, 16, 16, 64, 0, 128, 0),
+    (1, 3, 8, 8, 128, 0, 256, 0),
+    (2, 3, 7, 10, 16, 16, 16, 0),
+    (1, 17, 33, 18, 16, 0, 16, 0),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv3d_tcgen05_vs_oracle(cuda_dev, case):
+    N, D, H, W, c0, c1, co0, co1 = case
+    Cin, Cout = c0 + c1, co0 + co1
+    gen = torch.Generator().manual_seed(7)
+    x = torch.randn(N, Cin, D, H, W, generator=gen).bfloat16().float()
+    w = (torch.randn(Cout, Cin, 3, 3, 3, generator=gen) / (27 * Cin) ** 0.5).bfloat16().float()
+    b = torch.randn(Cout, generator=gen)
+    yr = TF.conv3d(x.double(), w.double(), b.double(), padding=1)
+    x0 = cl(x[:, :c0], torch.bfloat16)
+    x1 = cl(x[:, c0:], torch.bfloat16) if c1 else None
+    wp = F.pack_conv3_weights(w.to(cuda_dev), _lib.PACK_FPROP_TC, torch.bfloat16)
+    y0, y1 = F.conv3d_k3_raw(x0, x1, wp, b.to(cuda_dev), co0, co1, impl=2)
+    torch.cuda.synchronize()
+    y = cf(y0) if y1 is None else torch.cat([cf(y0), cf(y1)], dim=1)
+    assert rel_l2(y, yr) <= 4e-3  # bf16 output rounding (2^-9), fp32 accumulation
+    # identical inputs through the CUDA-core kernel: only accumulation order differs -> <= 1 bf16 ulp apart
+    wd = F.pack_conv3_weights(w.to(cuda_dev), _lib.PACK_FPROP, torch.bfloat16)
+    z0, z1 = F.conv3d_k3_raw(x0, x1, wd, b.to(cuda_dev), co0, co1, impl=1)
+    z = cf(z0) if z1 is None else torch.cat([cf(z0), cf(z1)], dim=1)
+    assert rel_l2(y, z) <= 3e-3
+    # dgrad packing: conv of a Cout-channel tensor back to Cin channels with flipped taps
+    gy = torch.randn(N, Cout, D, H, W, generator=gen).bfloat16().float()
+    xr = x.double().requires_grad_(True)
+    TF.conv3d(xr, w.double(), None, padding=1).backward(gy.double())
+    if Cin <= 128 or Cin % 128 == 0:
+        wpd = F.pack_conv3_weights(w.to(cuda_dev), _lib.PACK_DGRAD_TC, torch.bfloat16)
+        dx0, dx1 = F.conv3d_k3_raw(cl(gy, torch.bfloat16), None, wpd, None, c0, c1, impl=2)
+        dx = cf(dx0) if dx1 is None else torch.cat([cf(dx0), cf(dx1)], dim=1)
+        assert rel_l2(dx, xr.grad) <= 4e-3
