@@ -90,6 +90,9 @@ int64_t b200_pack_conv3_bytes(int mode, int dtype, int Cout, int Cin);
  * un-concat of the decoder's data gradient.  bias may be NULL.  impl: 0 = auto,
  * 1 = CUDA-core implicit GEMM, 2 = tcgen05/TMEM implicit GEMM (bf16, TC-packed weights).
  */
+/* resolves impl=0 (auto) for a given problem: returns 1 (CUDA-core, B200_PACK_FPROP/DGRAD weights) or
+ * 2 (tcgen05, B200_PACK_*_TC weights); the caller packs the weights accordingly. */
+int b200_conv3d_k3_select(int dtype, int impl, int c0, int c1, int co0, int co1, int N, int D, int H, int W);
 int b200_conv3d_k3(int dtype, int impl, const void* x0, int c0, const void* x1, int c1,
                    const void* wpack, const float* bias, void* y0, int co0, void* y1, int co1,
                    int N, int D, int H, int W, void* stream);

@@ -529,6 +529,11 @@ extern "C" int b200_pack_conv3_weights(int mode, int dtype, const float* w, void
   return B200_OK;
 }
 
+extern "C" int b200_conv3d_k3_select(int dtype, int impl, int c0, int c1, int co0, int co1, int N, int D, int H, int W) {
+  if (impl == 1 || impl == 2) return impl;
+  return (dtype == B200_BF16 && b200_conv3d_k3_tc_supported(c0, c1, co0, co1, N, D, H, W)) ? 2 : 1;
+}
+
 extern "C" int b200_conv3d_k3(int dtype, int impl, const void* x0, int c0, const void* x1, int c1, const void* wpack,
                               const float* bias, void* y0, int co0, void* y1, int co1, int N, int D, int H, int W,
                               void* stream) {
@@ -537,7 +542,9 @@ extern "C" int b200_conv3d_k3(int dtype, int impl, const void* x0, int c0, const
   B200_REQUIRE((c1 == 0) == (x1 == nullptr) && (co1 == 0) == (y1 == nullptr), B200_ERR_SHAPE, "conv3d_k3: second tensor / channel count mismatch");
   B200_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0, B200_ERR_SHAPE, "conv3d_k3: empty volume");
   cudaStream_t st = (cudaStream_t)stream;
-  if (impl == 2 || (impl == 0 && dtype == B200_BF16 && b200_conv3d_k3_tc_supported(c0, c1, co0, co1, N, D, H, W))) {
+  B200_REQUIRE(impl == 1 || impl == 2, B200_ERR_UNSUPPORTED,
+               "conv3d_k3: impl must be 1 (CUDA-core) or 2 (tcgen05); resolve 0 with b200_conv3d_k3_select so that the weights are packed to match");
+  if (impl == 2) {
     B200_REQUIRE(dtype == B200_BF16, B200_ERR_UNSUPPORTED, "conv3d_k3: tcgen05 path is bf16 only");
     return b200_conv3d_k3_tc(x0, c0, x1, c1, wpack, bias, y0, co0, y1, co1, N, D, H, W, st);
   }

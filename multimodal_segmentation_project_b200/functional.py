@@ -105,7 +105,21 @@ def pack_conv3_weights(weight: torch.Tensor, mode: int, dtype: torch.dtype) -> t
     return out
 
 
-def conv3d_k3_raw(x0, x1, wpack, bias, co0, co1=0, impl=0):
+def conv3d_select_impl(x0, x1, co0, co1, impl=0) -> int:
+    """1 = CUDA-core implicit GEMM, 2 = tcgen05; resolves 0 (auto) for this problem."""
+    L = _lib.load()
+    N, D, H, W, c0 = x0.shape
+    c1 = 0 if x1 is None else x1.shape[-1]
+    return L.b200_conv3d_k3_select(_dt(x0), impl, c0, c1, co0, co1, N, D, H, W)
+
+
+def pack_mode(impl: int, dgrad: bool) -> int:
+    if impl == 2:
+        return _lib.PACK_DGRAD_TC if dgrad else _lib.PACK_FPROP_TC
+    return _lib.PACK_DGRAD if dgrad else _lib.PACK_FPROP
+
+
+def conv3d_k3_raw(x0, x1, wpack, bias, co0, co1=0, impl=1):
     """3x3x3 'same' convolution of the virtual concat [x0|x1]; returns (y0, y1) with co0 / co1 channels."""
     L = _lib.load()
     N, D, H, W, c0 = x0.shape
@@ -153,12 +167,14 @@ class _ConvBNAct(torch.autograd.Function):
                 momentum, impl):
         _require_cuda(x0, x1, weight)
         L = _lib.load()
+        ctx.impl_req = impl
         x0 = x0.contiguous()
         x1 = None if x1 is None else x1.contiguous()
         N, D, H, W, _ = x0.shape
         Cout = weight.shape[0]
         dev = x0.device
-        wpack = pack_conv3_weights(weight, _lib.PACK_FPROP, x0.dtype)
+        impl = conv3d_select_impl(x0, x1, Cout, 0, impl)
+        wpack = pack_conv3_weights(weight, pack_mode(impl, False), x0.dtype)
         conv_out, _ = conv3d_k3_raw(x0, x1, wpack, _f32(bias), Cout, 0, impl)
         M, S = N * D * H * W, D * H * W
         if training and M <= 1:  # same contract as torch.nn.functional.batch_norm
@@ -183,7 +199,6 @@ class _ConvBNAct(torch.autograd.Function):
         )
         ctx.save_for_backward(x0, x1, weight, conv_out, stats, dropmask)
         ctx.training = bool(training)
-        ctx.impl = impl
         return y
 
     @staticmethod
@@ -218,8 +233,9 @@ class _ConvBNAct(torch.autograd.Function):
         if ctx.needs_input_grad[0] or (x1 is not None and ctx.needs_input_grad[1]):
             c0 = x0.shape[-1]
             c1 = 0 if x1 is None else x1.shape[-1]
-            wpack = pack_conv3_weights(weight, _lib.PACK_DGRAD, conv_out.dtype)
-            dx0, dx1 = conv3d_k3_raw(dconv, None, wpack, None, c0, c1, ctx.impl)
+            impl = conv3d_select_impl(dconv, None, c0, c1, ctx.impl_req)
+            wpack = pack_conv3_weights(weight, pack_mode(impl, True), conv_out.dtype)
+            dx0, dx1 = conv3d_k3_raw(dconv, None, wpack, None, c0, c1, impl)
         return (dx0, dx1, dw, db, dgamma, dbeta, None, None, None, None, None, None, None, None)
 
 

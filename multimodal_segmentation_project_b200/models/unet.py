@@ -84,7 +84,7 @@ def _compute_dtype(module, x):
     if forced is not None:
         return forced
     if torch.is_autocast_enabled():
-        if torch.get_autocast_gpu_dtype() == torch.float16 and not _warned_fp16:
+        if torch.get_autocast_dtype("cuda") == torch.float16 and not _warned_fp16:
             warnings.warn("fp16 autocast requested: libb200unet computes in bf16 (fp32 accumulate) instead")
             _warned_fp16 = True
         return torch.bfloat16
