@@ -100,6 +100,9 @@ int b200_conv3d_k3(int dtype, int impl, const void* x0, int c0, const void* x1, 
 /* weight gradient of nn.Conv3d(k=3,p=1): dw[Cout, Cin, 3,3,3] fp32 (torch layout, overwritten),
  * dbias[Cout] fp32 (may be NULL).  workspace: b200_conv3d_wgrad_workspace() bytes. */
 int64_t b200_conv3d_wgrad_workspace(int c0, int c1, int Cout, int N, int D, int H, int W);
+/* process-wide selection of the weight-gradient kernel: 0 auto (tcgen05 for bf16 when the channel
+ * counts allow), 1 CUDA-core split-K, 2 tcgen05 (error if unsupported) — for tests and benchmarks. */
+int b200_set_wgrad_impl(int impl);
 int b200_conv3d_wgrad(int dtype, const void* x0, int c0, const void* x1, int c1, const void* dy, int Cout,
                       float* dw, float* dbias, void* workspace, int64_t workspace_bytes,
                       int N, int D, int H, int W, void* stream);

@@ -506,6 +506,12 @@ int b200_conv3d_k3_tc(const void* x0, int c0, const void* x1, int c1, const void
 int b200_pack_conv3_weights_tc(int mode, const float* w, void* out, int Cout, int Cin, cudaStream_t stream);
 int64_t b200_pack_conv3_bytes_tc(int Cout, int Cin);
 bool b200_conv3d_k3_tc_supported(int c0, int c1, int co0, int co1, int N, int D, int H, int W);
+// tcgen05 weight gradient (wgrad_tc.cu)
+bool b200_conv3d_wgrad_tc_supported(int c0, int c1, int Cout, int N, int D, int H, int W);
+int64_t b200_conv3d_wgrad_tc_workspace(int c0, int c1, int Cout, int N, int D, int H, int W);
+int b200_conv3d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const void* dy, int Cout, float* dw, void* workspace,
+                         int N, int D, int H, int W, cudaStream_t stream);
+static int g_wgrad_impl = 0;  // 0 auto, 1 CUDA-core, 2 tcgen05
 
 // =========================================================================== exports
 extern "C" int64_t b200_pack_conv3_bytes(int mode, int dtype, int Cout, int Cin) {
@@ -570,10 +576,22 @@ extern "C" int b200_conv3d_k3(int dtype, int impl, const void* x0, int c0, const
   B200_FAIL(B200_ERR_UNSUPPORTED, "conv3d_k3: unknown dtype %d", dtype);
 }
 
+extern "C" int b200_set_wgrad_impl(int impl) {
+  B200_REQUIRE(impl >= 0 && impl <= 2, B200_ERR_UNSUPPORTED, "set_wgrad_impl: impl must be 0 (auto), 1 (CUDA-core) or 2 (tcgen05)");
+  g_wgrad_impl = impl;
+  return B200_OK;
+}
+
+// workspace layout: [bias partials][split-K partials of whichever kernel runs]
 extern "C" int64_t b200_conv3d_wgrad_workspace(int c0, int c1, int Cout, int N, int D, int H, int W) {
   const int R = 27 * (c0 + c1);
   const SplitPlan sp = plan_split((int64_t)N * D * H * W, R, Cout);
-  return (int64_t)sp.nsplit * R * Cout * 4 + b200_bn_partials_bytes(((Cout + 7) / 8) * 8);
+  int64_t main_bytes = (int64_t)sp.nsplit * R * Cout * 4;
+  if (b200_conv3d_wgrad_tc_supported(c0, c1, Cout, N, D, H, W)) {
+    const int64_t t = b200_conv3d_wgrad_tc_workspace(c0, c1, Cout, N, D, H, W);
+    if (t > main_bytes) main_bytes = t;
+  }
+  return b200_bn_partials_bytes(((Cout + 7) / 8) * 8) + main_bytes;
 }
 
 extern "C" int b200_conv3d_wgrad(int dtype, const void* x0, int c0, const void* x1, int c1, const void* dy, int Cout,
@@ -586,24 +604,31 @@ extern "C" int b200_conv3d_wgrad(int dtype, const void* x0, int c0, const void* 
   const Geom g{N, D, H, W};
   const int64_t M = g.rows();
   const int Cin = c0 + c1, R = 27 * Cin;
-  const SplitPlan sp = plan_split(M, R, Cout);
-  float* partial = (float*)workspace;
+  float* bpart = (float*)workspace;
+  float* partial = (float*)((uint8_t*)workspace + b200_bn_partials_bytes(((Cout + 7) / 8) * 8));
+  const bool tc_ok = dtype == B200_BF16 && b200_conv3d_wgrad_tc_supported(c0, c1, Cout, N, D, H, W);
+  B200_REQUIRE(g_wgrad_impl != 2 || tc_ok, B200_ERR_UNSUPPORTED, "conv3d_wgrad: tcgen05 path forced but unsupported for this problem");
   int rc;
-  if (dtype == B200_F32) {
-    rc = launch_cols_gemm("conv3d_wgrad", ColsK3<float>{(const float*)x0, (const float*)x1, c0, c1, g}, ColsDy<float>{(const float*)dy, Cout, g}, M, R, Cout, sp, partial, st);
-  } else if (dtype == B200_BF16) {
-    rc = launch_cols_gemm("conv3d_wgrad", ColsK3<__nv_bfloat16>{(const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, c0, c1, g},
-                          ColsDy<__nv_bfloat16>{(const __nv_bfloat16*)dy, Cout, g}, M, R, Cout, sp, partial, st);
+  if (tc_ok && g_wgrad_impl != 1) {
+    rc = b200_conv3d_wgrad_tc(x0, c0, x1, c1, dy, Cout, dw, partial, N, D, H, W, st);
+    if (rc) return rc;
   } else {
-    B200_FAIL(B200_ERR_UNSUPPORTED, "conv3d_wgrad: unknown dtype %d", dtype);
+    const SplitPlan sp = plan_split(M, R, Cout);
+    if (dtype == B200_F32) {
+      rc = launch_cols_gemm("conv3d_wgrad", ColsK3<float>{(const float*)x0, (const float*)x1, c0, c1, g}, ColsDy<float>{(const float*)dy, Cout, g}, M, R, Cout, sp, partial, st);
+    } else if (dtype == B200_BF16) {
+      rc = launch_cols_gemm("conv3d_wgrad", ColsK3<__nv_bfloat16>{(const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, c0, c1, g},
+                            ColsDy<__nv_bfloat16>{(const __nv_bfloat16*)dy, Cout, g}, M, R, Cout, sp, partial, st);
+    } else {
+      B200_FAIL(B200_ERR_UNSUPPORTED, "conv3d_wgrad: unknown dtype %d", dtype);
+    }
+    if (rc) return rc;
+    const int64_t total = (int64_t)R * Cout;
+    reduce_k3_wgrad_kernel<<<b200_grid_for(total, 256, B200_NUM_SMS * 8), 256, 0, st>>>(partial, sp.nsplit, Cin, Cout, dw);
+    B200_CHECK_LAUNCH("conv3d_wgrad_reduce");
   }
-  if (rc) return rc;
-  const int64_t total = (int64_t)R * Cout;
-  reduce_k3_wgrad_kernel<<<b200_grid_for(total, 256, B200_NUM_SMS * 8), 256, 0, st>>>(partial, sp.nsplit, Cin, Cout, dw);
-  B200_CHECK_LAUNCH("conv3d_wgrad_reduce");
   if (dbias) {
     B200_REQUIRE(Cout % 8 == 0, B200_ERR_UNSUPPORTED, "conv3d_wgrad: dbias needs Cout %% 8 == 0");
-    float* bpart = partial + (int64_t)sp.nsplit * R * Cout;
     return b200_channel_sum(dtype, dy, M, Cout, bpart, dbias, stream);
   }
   return B200_OK;

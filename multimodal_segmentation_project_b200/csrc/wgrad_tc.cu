@@ -1,0 +1,345 @@
+// wgrad_tc.cu — tcgen05 / TMEM weight gradient of the 3x3x3 convolution (bf16 in, fp32 out).
+//
+// Replaces cuDNN's bwd-filter kernel behind nn.Conv3d(k=3,p=1) (models/unet.py:11,15):
+//     dW[co][ci][kd][kh][kw] = sum_v  X[v + (kd-1, kh-1, kw-1)][ci] * dY[v][co]
+// The reduction runs over voxels, so voxels are the UMMA K dimension and BOTH operands are
+// "MN-major" (channels contiguous per voxel), which is exactly the NDHWC layout:
+//
+//   * P  = the tensor on the M side (<= 64 channels per CTA, no halo), staged per d-plane as
+//          [16-ch slab][16x16 voxels][16 ch]  (32-byte rows, SWIZZLE_32B)
+//   * Q  = the tensor on the N side (one 16-channel slab per CTA, 18x18 halo plane, row pitch 24
+//          voxels so every row starts on the 256-byte swizzle period), [voxel][16 ch], SWIZZLE_32B
+//   * one tcgen05.mma (M=64, N=48, K=16) per (row r of 16 voxels, kh): A = P[row r], B = Q[row r+kh]
+//     with the three kw taps expressed as the descriptor's leading-dimension stride (LBO = one
+//     voxel = 32 B), D[(kd,kh)] = 64 x (kw, 16 ch) fp32 in TMEM: 9 accumulators x 48 columns.
+//   * whichever of X / dY has more channels is put on the M side (it is the padded dimension);
+//     if that is X the result is the gradient of the mirrored tap, undone in the reduction.
+//   * every CTA owns 16x16xDSEG voxels x one Q slab x one 64-channel P chunk and writes its partial
+//     dW to a workspace; a second kernel reduces the partials in fixed order (deterministic).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int kQPitch = 24;                          // voxels per halo row (18 used), 768 B = 3 swizzle periods
+constexpr int kQBytes = 18 * kQPitch * 32;           // 13824
+constexpr int kPSlabBytes = 256 * 32;                // one 16-channel slab of a 16x16 plane
+constexpr int kQStages = 3, kPStages = 4;
+constexpr int kThreads = 288;                        // 4 producer + 4 epilogue + 1 MMA warps
+constexpr int kHeader = 256;
+constexpr int kAccCols = 9 * 48;                     // 432 -> 512 allocated
+constexpr int kMaxDseg = 16;
+
+struct WgParams {
+  const bf16* p; int cp;        // M-side tensor [N,D,H,W,cp]
+  const bf16* q0; const bf16* q1; int cq0, cq1;  // N-side tensor = virtual concat [q0 | q1]
+  float* partial;               // [cta][mrows][27][16]
+  int mrows;                    // min(64, cp): rows stored per CTA
+  int N, D, H, W;
+  int mslabs;                   // 16-channel slabs of P handled per CTA (1..4)
+  int dseg, dblocks, tiles_w, tiles_h;
+};
+
+__device__ __forceinline__ uint32_t swz32(uint32_t off) { return off ^ (((off >> 7) & 1u) << 4); }
+
+__device__ __forceinline__ uint64_t desc_mn_sw32(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                       // version
+  d |= (uint64_t)((addr >> 7) & 0x7) << 49;     // base offset (0 for 256-byte aligned starts)
+  d |= (uint64_t)6 << 61;                       // SWIZZLE_32B
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const WgParams g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // SWIZZLE_32B patterns repeat every 256 bytes of ABSOLUTE shared-memory address: align the carve-up ourselves
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t bar0 = tc::smem_u32(bars);
+  auto q_full = [&](int i) { return bar0 + 8u * i; };
+  auto q_empty = [&](int i) { return bar0 + 8u * (3 + i); };
+  auto p_full = [&](int i) { return bar0 + 8u * (6 + i); };
+  auto p_empty = [&](int i) { return bar0 + 8u * (10 + i); };
+  const uint32_t acc_done = bar0 + 8u * 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 192);
+  uint8_t* pbuf = smem + kHeader;                                   // kPStages x mslabs x 8192
+  const uint32_t p_stage_bytes = (uint32_t)g.mslabs * kPSlabBytes;
+  uint8_t* qbuf = pbuf + kPStages * p_stage_bytes;                  // kQStages x 13824
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tw = blockIdx.x % g.tiles_w, th = blockIdx.x / g.tiles_w % g.tiles_h;
+  const int rest = blockIdx.x / (g.tiles_w * g.tiles_h);
+  const int n = rest / g.dblocks, db = rest % g.dblocks;
+  const int mchunk = blockIdx.y;      // 64-channel chunk of P
+  const int qslab = blockIdx.z;       // 16-channel slab of Q
+  const int w0 = tw * 16, h0 = th * 16, d0 = db * g.dseg;
+  const int planes = min(g.dseg, g.D - d0);
+
+  if (warp == 8 && lane == 0) {
+    for (int i = 0; i < kQStages; ++i) { tc::mbar_init(q_full(i), 4); tc::mbar_init(q_empty(i), 1); }
+    for (int i = 0; i < kPStages; ++i) { tc::mbar_init(p_full(i), 4); tc::mbar_init(p_empty(i), 1); }
+    tc::mbar_init(acc_done, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 4) {
+    tc::tmem_alloc(tc::smem_u32(tmem_slot), 512);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== producers =====================
+    const int tid = threadIdx.x;
+    const int cpo = mchunk * 64;                       // first P channel of this CTA
+    const int pieces = g.mslabs * 2;                   // 16-byte pieces per P voxel
+    const int qc = qslab * 16;
+    const bf16* qbase; int qcs, qoff;
+    if (qc < g.cq0) { qbase = g.q0; qcs = g.cq0; qoff = qc; } else { qbase = g.q1; qcs = g.cq1; qoff = qc - g.cq0; }
+    int pcount = 0, qcount = 0;
+    for (int i = 0; i <= planes + 1; ++i) {
+      if (i < planes) {
+        // ---- P plane i : 16x16 voxels x (mslabs*16) channels
+        const int st = pcount % kPStages;
+        tc::mbar_wait(p_empty(st), ((pcount / kPStages) & 1) ^ 1);
+        uint8_t* dst = pbuf + st * p_stage_bytes;
+        const int d = d0 + i;
+        const int items = 256 * pieces;
+        for (int base = 0; base < items; base += 128 * 8) {
+          uint4 v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int id = base + tid + 128 * j;
+            v[j] = make_uint4(0, 0, 0, 0);
+            if (id < items) {
+              const int vox = id / pieces, pc = id - vox * pieces;
+              const int h = h0 + (vox >> 4), w = w0 + (vox & 15);
+              if (h < g.H && w < g.W && cpo + pc * 8 < g.cp) {
+                const int64_t row = (((int64_t)n * g.D + d) * g.H + h) * g.W + w;
+                v[j] = __ldg(reinterpret_cast<const uint4*>(g.p + row * g.cp + cpo + pc * 8));
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int id = base + tid + 128 * j;
+            if (id < items) {
+              const int vox = id / pieces, pc = id - vox * pieces;
+              const uint32_t off = (uint32_t)(pc >> 1) * kPSlabBytes + swz32((uint32_t)vox * 32 + (pc & 1) * 16);
+              *reinterpret_cast<uint4*>(dst + off) = v[j];
+            }
+          }
+        }
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(p_full(st));
+        ++pcount;
+      }
+      {
+        // ---- Q plane q = i - 1 : 18x18 halo voxels x 16 channels
+        const int q = i - 1;
+        const int st = qcount % kQStages;
+        tc::mbar_wait(q_empty(st), ((qcount / kQStages) & 1) ^ 1);
+        uint8_t* dst = qbuf + st * kQBytes;
+        const int d = d0 + q;
+        const bool dvalid = (unsigned)d < (unsigned)g.D;
+        uint4 v[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const int id = tid + 128 * j;
+          v[j] = make_uint4(0, 0, 0, 0);
+          if (id < 648) {
+            const int vox = id >> 1, pc = id & 1;
+            const int hh = vox / 18, ww = vox - hh * 18;
+            const int h = h0 + hh - 1, w = w0 + ww - 1;
+            if (dvalid && (unsigned)h < (unsigned)g.H && (unsigned)w < (unsigned)g.W) {
+              const int64_t row = (((int64_t)n * g.D + d) * g.H + h) * g.W + w;
+              v[j] = __ldg(reinterpret_cast<const uint4*>(qbase + row * qcs + qoff + pc * 8));
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const int id = tid + 128 * j;
+          if (id < 648) {
+            const int vox = id >> 1, pc = id & 1;
+            const int hh = vox / 18, ww = vox - hh * 18;
+            *reinterpret_cast<uint4*>(dst + swz32((uint32_t)(hh * kQPitch + ww) * 32 + pc * 16)) = v[j];
+          }
+        }
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(q_full(st));
+        ++qcount;
+      }
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issue =====================
+    if (lane == 0) {
+      // M = 64, N = 48, A and B MN-major
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((48u >> 3) << 17) | ((64u >> 4) << 24);
+      const uint32_t a_lbo = g.mslabs > 1 ? kPSlabBytes : 0;   // M-group (16 ch) stride; rows beyond the real channels are ignored
+      uint32_t touched = 0;
+      int p_ready = 0;  // number of P planes whose full-barrier has been observed
+      for (int qi = 0; qi <= planes + 1; ++qi) {
+        const int q = qi - 1;
+        const int qst = qi % kQStages;
+        tc::mbar_wait(q_full(qst), (qi / kQStages) & 1);
+        const int need = min(q + 2, planes);  // planes 0 .. q+1 must have landed
+        while (p_ready < need) {
+          tc::mbar_wait(p_full(p_ready % kPStages), (p_ready / kPStages) & 1);
+          ++p_ready;
+        }
+        tc::tc_fence_after();
+        const uint32_t q_base = tc::smem_u32(qbuf + qst * kQBytes);
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd) {
+          const int pl = q - kd + 1;
+          if (pl < 0 || pl >= planes) continue;
+          const uint32_t p_base = tc::smem_u32(pbuf + (pl % kPStages) * p_stage_bytes);
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)((kd * 3 + kh) * 48);
+            uint32_t acc = (touched >> (kd * 3 + kh)) & 1u;
+            for (int r = 0; r < 16; ++r) {
+              const uint64_t adesc = desc_mn_sw32(p_base + r * 512, a_lbo, 256);
+              const uint64_t bdesc = desc_mn_sw32(q_base + (r + kh) * (kQPitch * 32), 32, 256);
+              tc::umma_bf16_ss(d_tmem, adesc, bdesc, idesc, acc);
+              acc = 1;
+            }
+            touched |= 1u << (kd * 3 + kh);
+          }
+        }
+        tc::umma_commit(q_empty(qst));
+        if (q - 1 >= 0 && q - 1 < planes) tc::umma_commit(p_empty((q - 1) % kPStages));  // plane q-1 was last used here (kd = 2)
+      }
+      tc::umma_commit(acc_done);
+    }
+  } else {
+    // ===================== epilogue: TMEM -> partial dW =====================
+    const int ew = warp - 4;
+    tc::mbar_wait(acc_done, 0);
+    tc::tc_fence_after();
+    const int m_real = min(64, g.cp - mchunk * 64);
+    const int co = ew * 16 + lane;  // M=64 accumulators: row m lives in TMEM lane (m % 16) + 32 * (m / 16)
+    const int64_t cta = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    float* out = g.partial + cta * (int64_t)(g.mrows * 27 * 16);
+    for (int t9 = 0; t9 < 9; ++t9) {
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        uint32_t r[16];
+        tc::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(t9 * 48 + kw * 16), r);
+        tc::tmem_ld_wait();
+        if (lane < 16 && co < m_real) {
+          float4* dst = reinterpret_cast<float4*>(out + ((int64_t)co * 27 + t9 * 3 + kw) * 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// partial[(qslab, mchunk, spatial cta)][m 64][tap 27][n 16] -> dw[co][ci][27]
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int spatial, int mchunks, int mrows, int Cout, int Cin,
+                                       int swapped, float* __restrict__ dw) {
+  const int64_t stride = (int64_t)mrows * 27 * 16;
+  const int64_t total = (int64_t)Cout * Cin * 27;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % 27);
+    const int ci = (int)((i / 27) % Cin);
+    const int co = (int)(i / (27 * (int64_t)Cin));
+    // M side = dY (co) and N side = X (ci) unless swapped; swapped results carry the mirrored tap
+    const int m = swapped ? ci : co, nn = swapped ? co : ci;
+    const int t = swapped ? 26 - tap : tap;
+    const int mchunk = m / 64, mm = m % 64, qslab = nn / 16, nl = nn % 16;
+    const float* src = partial + (((int64_t)qslab * mchunks + mchunk) * spatial) * stride + ((int64_t)mm * 27 + t) * 16 + nl;
+    double s = 0.0;
+    for (int c = 0; c < spatial; ++c) s += (double)src[(int64_t)c * stride];
+    dw[i] = (float)s;
+  }
+}
+
+struct WgPlan { int swapped, cp, cq, mslabs, mchunks, qslabs, dseg, dblocks, tiles_w, tiles_h, spatial; size_t smem; };
+
+WgPlan make_plan(int c0, int c1, int Cout, int N, int D, int H, int W) {
+  WgPlan pl;
+  const int Cin = c0 + c1;
+  // the M side is padded to 64 rows: give it the wider tensor.  A concatenated X stays on the N side.
+  pl.swapped = (c1 == 0 && Cin > Cout) ? 1 : 0;
+  pl.cp = pl.swapped ? Cin : Cout;
+  pl.cq = pl.swapped ? Cout : Cin;
+  pl.mchunks = (pl.cp + 63) / 64;
+  pl.mslabs = pl.cp >= 64 ? 4 : pl.cp / 16;
+  pl.qslabs = pl.cq / 16;
+  pl.tiles_w = (W + 15) / 16;
+  pl.tiles_h = (H + 15) / 16;
+  // enough CTAs to fill the machine a few times, but long d-runs to amortise the 432-column epilogue
+  const int64_t base = (int64_t)pl.tiles_w * pl.tiles_h * N * pl.mchunks * pl.qslabs;
+  int dseg = kMaxDseg;
+  while (dseg > 2 && base * ((D + dseg - 1) / dseg) < 2 * B200_NUM_SMS) dseg >>= 1;
+  if (dseg > D) dseg = D;
+  pl.dseg = dseg;
+  pl.dblocks = (D + dseg - 1) / dseg;
+  pl.spatial = pl.tiles_w * pl.tiles_h * N * pl.dblocks;
+  pl.smem = kHeader + (size_t)kPStages * pl.mslabs * kPSlabBytes + (size_t)kQStages * kQBytes + 1024;
+  return pl;
+}
+
+}  // namespace
+
+bool b200_conv3d_wgrad_tc_supported(int c0, int c1, int Cout, int N, int D, int H, int W) {
+  if (c0 <= 0 || c0 % 16 || c1 % 16 || Cout % 16) return false;
+  const int Cin = c0 + c1;
+  if ((Cin > 64 && Cin % 64) || (Cout > 64 && Cout % 64)) return false;
+  return N > 0 && D > 0 && H > 0 && W > 0;
+}
+
+int64_t b200_conv3d_wgrad_tc_workspace(int c0, int c1, int Cout, int N, int D, int H, int W) {
+  const WgPlan pl = make_plan(c0, c1, Cout, N, D, H, W);
+  return (int64_t)pl.spatial * pl.mchunks * pl.qslabs * (pl.cp < 64 ? pl.cp : 64) * 27 * 16 * 4;
+}
+
+int b200_conv3d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const void* dy, int Cout, float* dw, void* workspace,
+                         int N, int D, int H, int W, cudaStream_t stream) {
+  B200_REQUIRE(b200_conv3d_wgrad_tc_supported(c0, c1, Cout, N, D, H, W), B200_ERR_UNSUPPORTED, "conv3d_wgrad(tcgen05): unsupported channel counts");
+  const WgPlan pl = make_plan(c0, c1, Cout, N, D, H, W);
+  WgParams g;
+  if (pl.swapped) {
+    g.p = (const bf16*)x0; g.cp = c0;
+    g.q0 = (const bf16*)dy; g.q1 = nullptr; g.cq0 = Cout; g.cq1 = 0;
+  } else {
+    g.p = (const bf16*)dy; g.cp = Cout;
+    g.q0 = (const bf16*)x0; g.q1 = (const bf16*)x1; g.cq0 = c0; g.cq1 = c1;
+  }
+  g.partial = (float*)workspace;
+  g.mrows = pl.cp < 64 ? pl.cp : 64;
+  g.N = N; g.D = D; g.H = H; g.W = W;
+  g.mslabs = pl.mslabs; g.dseg = pl.dseg; g.dblocks = pl.dblocks; g.tiles_w = pl.tiles_w; g.tiles_h = pl.tiles_h;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  B200_REQUIRE(pl.mchunks <= 65535 && pl.qslabs <= 65535, B200_ERR_UNSUPPORTED, "conv3d_wgrad(tcgen05): grid too large");
+  dim3 grid((unsigned)pl.spatial, (unsigned)pl.mchunks, (unsigned)pl.qslabs);
+  wgrad_tc_kernel<<<grid, kThreads, pl.smem, stream>>>(g);
+  B200_CHECK_LAUNCH("conv3d_wgrad_tc");
+  const int64_t total = (int64_t)Cout * (c0 + c1) * 27;
+  wgrad_tc_reduce_kernel<<<b200_grid_for(total, 256, B200_NUM_SMS * 8), 256, 0, stream>>>((const float*)workspace, pl.spatial, pl.mchunks, g.mrows,
+                                                                                        Cout, c0 + c1, pl.swapped, dw);
+  B200_CHECK_LAUNCH("conv3d_wgrad_tc_reduce");
+  return B200_OK;
+}

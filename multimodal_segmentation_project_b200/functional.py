@@ -151,6 +151,11 @@ def conv3d_wgrad_raw(x0, x1, dy, want_bias=True):
     return dw, db
 
 
+def set_wgrad_impl(impl: int) -> None:
+    """0 auto, 1 CUDA-core split-K, 2 tcgen05 (process-wide; tests and benchmarks)."""
+    check(_lib.load().b200_set_wgrad_impl(int(impl)), "set_wgrad_impl")
+
+
 def _bn_partials(C, device):
     L = _lib.load()
     return torch.empty(L.b200_bn_partials_bytes(C) // 4, dtype=torch.float32, device=device)

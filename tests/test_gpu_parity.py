@@ -605,3 +605,39 @@ def test_conv3d_tcgen05_vs_oracle(cuda_dev, case):
         dx0, dx1 = F.conv3d_k3_raw(cl(gy, torch.bfloat16), None, wpd, None, c0, c1, impl=2)
         dx = cf(dx0) if dx1 is None else torch.cat([cf(dx0), cf(dx1)], dim=1)
         assert rel_l2(dx, xr.grad) <= 4e-3
+
+
+WG_CASES = [
+    # N, D, H, W, c0, c1, Cout
+    (1, 8, 16, 16, 16, 0, 16),
+    (2, 5, 20, 24, 16, 0, 32),
+    (1, 6, 12, 16, 32, 0, 16),      # Cin > Cout: X goes to the M side (mirrored taps)
+    (1, 4, 8, 8, 32, 32, 32),       # concat input
+    (1, 4, 16, 16, 64, 0, 128),
+    (1, 3, 8, 8, 128, 0, 256),
+    (1, 3, 8, 8, 256, 0, 128),
+    (1, 19, 33, 18, 16, 0, 16),
+]
+
+
+@pytest.mark.parametrize("case", WG_CASES)
+def test_conv3d_wgrad_tcgen05_vs_oracle(cuda_dev, case):
+    N, D, H, W, c0, c1, Cout = case
+    Cin = c0 + c1
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn(N, Cin, D, H, W, generator=gen).bfloat16().float()
+    gy = torch.randn(N, Cout, D, H, W, generator=gen).bfloat16().float()
+    w = torch.zeros(Cout, Cin, 3, 3, 3, dtype=torch.float64, requires_grad=True)
+    TF.conv3d(x.double(), w, None, padding=1).backward(gy.double())
+    x0 = cl(x[:, :c0], torch.bfloat16)
+    x1 = cl(x[:, c0:], torch.bfloat16) if c1 else None
+    dy = cl(gy, torch.bfloat16)
+    try:
+        F.set_wgrad_impl(2)
+        dw, db = F.conv3d_wgrad_raw(x0, x1, dy, want_bias=True)
+        torch.cuda.synchronize()
+    finally:
+        F.set_wgrad_impl(0)
+    # bf16-exact inputs, fp32 accumulation in TMEM, fp64 fixed-order split-K reduction
+    assert rel_l2(dw, w.grad) <= 2e-5
+    assert rel_l2(db, gy.double().sum(dim=(0, 2, 3, 4))) <= 2e-5

@@ -25,7 +25,7 @@ def timeit(fn, iters=5, flush=None):
 def main():
     dev = torch.device("cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    impls = [int(a) for a in sys.argv[1:]] or [2, 1]
+    impls = [int(a) for a in sys.argv[1:] if a.isdigit()] or [2]
     rows = []
     for name, S, Cin, Cout in LAYERS:
         N = 2
@@ -38,6 +38,17 @@ def main():
             wp = F.pack_conv3_weights(w, _lib.PACK_FPROP_TC if impl == 2 else _lib.PACK_FPROP, torch.bfloat16)
             ms = timeit(lambda: F.conv3d_k3_raw(x, None, wp, b, Cout, 0, impl=impl), flush=flush)
             row[f"impl{impl}_ms"] = ms; row[f"impl{impl}_tflops"] = flops / ms / 1e9
+        dy = torch.randn(N, S, S, S, Cout, device=dev).bfloat16()
+        for wi in (2, 1):
+            if wi == 1 and S >= 64 and "--slow" not in sys.argv:
+                continue
+            F.set_wgrad_impl(wi)
+            try:
+                ms = timeit(lambda: F.conv3d_wgrad_raw(x, None, dy, want_bias=False), flush=flush)
+                row[f"wgrad{wi}_ms"] = ms; row[f"wgrad{wi}_tflops"] = flops / ms / 1e9
+            except Exception as e:
+                row[f"wgrad{wi}_err"] = str(e)[:80]
+            F.set_wgrad_impl(0)
         xt = x.permute(0, 4, 1, 2, 3)  # NCDHW view of channels-last memory
         wt = w.bfloat16().contiguous(memory_format=torch.channels_last_3d)
         ms = timeit(lambda: torch.nn.functional.conv3d(xt, wt, b.bfloat16(), padding=1), flush=flush)
