@@ -512,6 +512,12 @@ int64_t b200_conv3d_wgrad_tc_workspace(int c0, int c1, int Cout, int N, int D, i
 int b200_conv3d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const void* dy, int Cout, float* dw, void* workspace,
                          int N, int D, int H, int W, cudaStream_t stream);
 static int g_wgrad_impl = 0;  // 0 auto, 1 CUDA-core, 2 tcgen05
+// in_channels == 1 first layer (conv_stem.cu)
+bool b200_conv_stem_supported(int c0, int c1, int cout);
+bool b200_conv_stem_wgrad_supported(int c0, int c1, int cout);
+int b200_conv_stem_fwd(int dtype, const void* x, const void* wpack, const float* bias, void* y, int cout, int N, int D, int H, int W, cudaStream_t st);
+int64_t b200_conv_stem_wgrad_workspace(int cout);
+int b200_conv_stem_wgrad(int dtype, const void* x, const void* dy, int cout, float* dw, float* partials, int N, int D, int H, int W, cudaStream_t st);
 
 // =========================================================================== exports
 extern "C" int64_t b200_pack_conv3_bytes(int mode, int dtype, int Cout, int Cin) {
@@ -554,6 +560,8 @@ extern "C" int b200_conv3d_k3(int dtype, int impl, const void* x0, int c0, const
     B200_REQUIRE(dtype == B200_BF16, B200_ERR_UNSUPPORTED, "conv3d_k3: tcgen05 path is bf16 only");
     return b200_conv3d_k3_tc(x0, c0, x1, c1, wpack, bias, y0, co0, y1, co1, N, D, H, W, st);
   }
+  if (co1 == 0 && b200_conv_stem_supported(c0, c1, co0) && (dtype == B200_F32 || dtype == B200_BF16))
+    return b200_conv_stem_fwd(dtype, x0, wpack, bias, y0, co0, N, D, H, W, st);
   const Geom g{N, D, H, W};
   const int64_t M = g.rows();
   const int Cin = c0 + c1, Cout = co0 + co1;
@@ -591,6 +599,8 @@ extern "C" int64_t b200_conv3d_wgrad_workspace(int c0, int c1, int Cout, int N, 
     const int64_t t = b200_conv3d_wgrad_tc_workspace(c0, c1, Cout, N, D, H, W);
     if (t > main_bytes) main_bytes = t;
   }
+  if (b200_conv_stem_wgrad_supported(c0, c1, Cout) && b200_conv_stem_wgrad_workspace(Cout) > main_bytes)
+    main_bytes = b200_conv_stem_wgrad_workspace(Cout);
   return b200_bn_partials_bytes(((Cout + 7) / 8) * 8) + main_bytes;
 }
 
@@ -609,7 +619,10 @@ extern "C" int b200_conv3d_wgrad(int dtype, const void* x0, int c0, const void* 
   const bool tc_ok = dtype == B200_BF16 && b200_conv3d_wgrad_tc_supported(c0, c1, Cout, N, D, H, W);
   B200_REQUIRE(g_wgrad_impl != 2 || tc_ok, B200_ERR_UNSUPPORTED, "conv3d_wgrad: tcgen05 path forced but unsupported for this problem");
   int rc;
-  if (tc_ok && g_wgrad_impl != 1) {
+  if (b200_conv_stem_wgrad_supported(c0, c1, Cout) && (dtype == B200_F32 || dtype == B200_BF16)) {
+    rc = b200_conv_stem_wgrad(dtype, x0, dy, Cout, dw, partial, N, D, H, W, st);
+    if (rc) return rc;
+  } else if (tc_ok && g_wgrad_impl != 1) {
     rc = b200_conv3d_wgrad_tc(x0, c0, x1, c1, dy, Cout, dw, partial, N, D, H, W, st);
     if (rc) return rc;
   } else {

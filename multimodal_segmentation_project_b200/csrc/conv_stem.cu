@@ -1,0 +1,219 @@
+// conv_stem.cu — the network's first convolution: nn.Conv3d(1, 16, k=3, p=1) (models/unet.py:11 via
+// encoder[0]), in_channels == 1.  K = 27 only, so this layer is HBM-bound on its 16-channel output
+// (134 MB at 2x128^3) and runs on the CUDA cores:
+//   * forward : one thread = 2 adjacent voxels x all Cout channels, input halo tile in shared memory,
+//               weights broadcast from shared memory, 32-byte vector stores of the NDHWC output;
+//   * wgrad   : dW[co][tap] = sum_v x[v+tap] dy[v][co] — persistent CTAs, each thread owns a
+//               (kd, kh, 4-channel) slice with 3 kw x 4 co register accumulators and streams an
+//               8x8x8 voxel tile out of shared memory; per-CTA partials are reduced in fixed order.
+// (No data gradient: the network input does not require one.)
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxCout = 32;
+
+// ------------------------------------------------------------------ forward
+constexpr int FT_W = 64, FT_H = 8;               // output tile per CTA: 64 (w) x 8 (h) x 1 (d)
+constexpr int FX_W = FT_W + 2, FX_H = FT_H + 2;  // halo tile
+constexpr int kFwdThreads = 256;                 // 32 (w pairs) x 8 (h)
+
+template <typename T, int COUT>
+__global__ void __launch_bounds__(kFwdThreads)
+stem_fwd_kernel(const T* __restrict__ x, const T* __restrict__ wpack /*[27][COUT]*/, const float* __restrict__ bias,
+                T* __restrict__ y, int N, int D, int H, int W, int tiles_w, int tiles_h) {
+  __shared__ float xs[3][FX_H][FX_W + 2];
+  __shared__ __align__(16) float ws[27][COUT];
+  const int tw = blockIdx.x % tiles_w, th = blockIdx.x / tiles_w % tiles_h;
+  const int nd = blockIdx.x / (tiles_w * tiles_h);
+  const int n = nd / D, d = nd % D;
+  const int w0 = tw * FT_W, h0 = th * FT_H;
+  for (int i = threadIdx.x; i < 27 * COUT; i += kFwdThreads) ws[i / COUT][i % COUT] = to_f32<T>(wpack[i]);
+  for (int i = threadIdx.x; i < 3 * FX_H * FX_W; i += kFwdThreads) {
+    const int ww = i % FX_W, hh = (i / FX_W) % FX_H, dd = i / (FX_W * FX_H);
+    const int gd = d + dd - 1, gh = h0 + hh - 1, gw = w0 + ww - 1;
+    float v = 0.f;
+    if ((unsigned)gd < (unsigned)D && (unsigned)gh < (unsigned)H && (unsigned)gw < (unsigned)W)
+      v = to_f32<T>(x[(((int64_t)n * D + gd) * H + gh) * W + gw]);
+    xs[dd][hh][ww] = v;
+  }
+  __syncthreads();
+  const int lw = (threadIdx.x & 31) * 2, lh = threadIdx.x >> 5;
+  float acc0[COUT], acc1[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc0[c] = acc1[c] = bias ? bias[c] : 0.f;
+#pragma unroll
+  for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const float* row = &xs[kd][lh + kh][lw];
+      const float x0 = row[0], x1 = row[1], x2 = row[2], x3 = row[3];
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const float a = kw == 0 ? x0 : (kw == 1 ? x1 : x2);
+        const float b = kw == 0 ? x1 : (kw == 1 ? x2 : x3);
+        const int tap = kd * 9 + kh * 3 + kw;
+#pragma unroll
+        for (int c4 = 0; c4 < COUT / 4; ++c4) {
+          const float4 wv = *reinterpret_cast<const float4*>(&ws[tap][c4 * 4]);
+          acc0[c4 * 4 + 0] = fmaf(a, wv.x, acc0[c4 * 4 + 0]); acc1[c4 * 4 + 0] = fmaf(b, wv.x, acc1[c4 * 4 + 0]);
+          acc0[c4 * 4 + 1] = fmaf(a, wv.y, acc0[c4 * 4 + 1]); acc1[c4 * 4 + 1] = fmaf(b, wv.y, acc1[c4 * 4 + 1]);
+          acc0[c4 * 4 + 2] = fmaf(a, wv.z, acc0[c4 * 4 + 2]); acc1[c4 * 4 + 2] = fmaf(b, wv.z, acc1[c4 * 4 + 2]);
+          acc0[c4 * 4 + 3] = fmaf(a, wv.w, acc0[c4 * 4 + 3]); acc1[c4 * 4 + 3] = fmaf(b, wv.w, acc1[c4 * 4 + 3]);
+        }
+      }
+    }
+  const int gh = h0 + lh, gw = w0 + lw;
+  if (gh < H) {
+    const int64_t row = (((int64_t)n * D + d) * H + gh) * W + gw;
+#pragma unroll
+    for (int c8 = 0; c8 < COUT / 8; ++c8) {
+      float f[8];
+      if (gw < W) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = acc0[c8 * 8 + i];
+        Vec8<T> v; v.set(f); v.store(y + row * COUT + c8 * 8);
+      }
+      if (gw + 1 < W) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = acc1[c8 * 8 + i];
+        Vec8<T> v; v.set(f); v.store(y + (row + 1) * COUT + c8 * 8);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ weight gradient
+constexpr int WT = 8;                              // 8 x 8 x 8 voxel tile
+constexpr int kWgMaxBlocks = 592;
+
+template <typename T, int COUT>
+__global__ void __launch_bounds__(8 * 9 * (COUT / 4))
+stem_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ partials /*[blocks][27*COUT]*/,
+                  int N, int D, int H, int W, int tiles_w, int tiles_h, int tiles_d) {
+  constexpr int CQ = COUT / 4;            // channel quads
+  constexpr int TPG = 9 * CQ;             // threads per group: (kd, kh) x quad
+  __shared__ float xs[WT + 2][WT + 2][WT + 4];
+  __shared__ __align__(16) float ds[WT * WT * WT][COUT];
+  const int grp = threadIdx.x / TPG, t = threadIdx.x % TPG;   // group = d-plane of the tile
+  const int kd = t / (3 * CQ), kh = (t / CQ) % 3, cq = t % CQ;
+  float acc[3][4];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int64_t ntiles = (int64_t)N * tiles_d * tiles_h * tiles_w;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int64_t r = tile;
+    const int tw = (int)(r % tiles_w); r /= tiles_w;
+    const int th = (int)(r % tiles_h); r /= tiles_h;
+    const int td = (int)(r % tiles_d);
+    const int n = (int)(r / tiles_d);
+    const int w0 = tw * WT, h0 = th * WT, d0 = td * WT;
+    __syncthreads();
+    for (int i = threadIdx.x; i < (WT + 2) * (WT + 2) * (WT + 2); i += blockDim.x) {
+      const int ww = i % (WT + 2), hh = (i / (WT + 2)) % (WT + 2), dd = i / ((WT + 2) * (WT + 2));
+      const int gd = d0 + dd - 1, gh = h0 + hh - 1, gw = w0 + ww - 1;
+      float v = 0.f;
+      if ((unsigned)gd < (unsigned)D && (unsigned)gh < (unsigned)H && (unsigned)gw < (unsigned)W)
+        v = to_f32<T>(x[(((int64_t)n * D + gd) * H + gh) * W + gw]);
+      xs[dd][hh][ww] = v;
+    }
+    for (int i = threadIdx.x; i < WT * WT * WT * (COUT / 8); i += blockDim.x) {
+      const int c8 = i % (COUT / 8), vox = i / (COUT / 8);
+      const int ww = vox % WT, hh = (vox / WT) % WT, dd = vox / (WT * WT);
+      const int gd = d0 + dd, gh = h0 + hh, gw = w0 + ww;
+      float f[8];
+      if (gd < D && gh < H && gw < W) {
+        Vec8<T> v;
+        v.load(dy + ((((int64_t)n * D + gd) * H + gh) * W + gw) * COUT + c8 * 8);
+        v.get(f);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ds[vox][c8 * 8 + k] = f[k];
+    }
+    __syncthreads();
+    // group grp streams d-plane grp of the tile
+#pragma unroll 2
+    for (int hh = 0; hh < WT; ++hh) {
+      const float* xr = &xs[grp + kd][hh + kh][0];
+      float xa = xr[0], xb = xr[1];
+#pragma unroll
+      for (int ww = 0; ww < WT; ++ww) {
+        const float xc = xr[ww + 2];
+        const float4 g = *reinterpret_cast<const float4*>(&ds[(grp * WT + hh) * WT + ww][cq * 4]);
+        acc[0][0] = fmaf(xa, g.x, acc[0][0]); acc[0][1] = fmaf(xa, g.y, acc[0][1]); acc[0][2] = fmaf(xa, g.z, acc[0][2]); acc[0][3] = fmaf(xa, g.w, acc[0][3]);
+        acc[1][0] = fmaf(xb, g.x, acc[1][0]); acc[1][1] = fmaf(xb, g.y, acc[1][1]); acc[1][2] = fmaf(xb, g.z, acc[1][2]); acc[1][3] = fmaf(xb, g.w, acc[1][3]);
+        acc[2][0] = fmaf(xc, g.x, acc[2][0]); acc[2][1] = fmaf(xc, g.y, acc[2][1]); acc[2][2] = fmaf(xc, g.z, acc[2][2]); acc[2][3] = fmaf(xc, g.w, acc[2][3]);
+        xa = xb; xb = xc;
+      }
+    }
+  }
+  // reduce the 8 groups through shared memory (reuse ds), then one partial row per CTA
+  __syncthreads();
+  float* red = &ds[0][0];  // [8][27*COUT]
+#pragma unroll
+  for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[grp * (27 * COUT) + (kd * 9 + kh * 3 + kw) * COUT + cq * 4 + j] = acc[kw][j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int gi = 0; gi < 8; ++gi) s += red[gi * (27 * COUT) + i];
+    partials[(int64_t)blockIdx.x * (27 * COUT) + i] = s;
+  }
+}
+
+// partials[b][tap][co] -> dw[co][0][tap]
+__global__ void stem_wgrad_finalize_kernel(const float* __restrict__ partials, int nblocks, int Cout, float* __restrict__ dw) {
+  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (o >= 27 * Cout) return;
+  const int tap = o % 27, co = o / 27;
+  double s = 0.0;
+  for (int b = lane; b < nblocks; b += 32) s += (double)partials[(int64_t)b * 27 * Cout + tap * Cout + co];
+  s = warp_sum_d(s);
+  if (lane == 0) dw[o] = (float)s;
+}
+
+inline int wg_blocks(int N, int D, int H, int W) {
+  const int64_t tiles = (int64_t)N * ((D + WT - 1) / WT) * ((H + WT - 1) / WT) * ((W + WT - 1) / WT);
+  return (int)(tiles < kWgMaxBlocks ? tiles : kWgMaxBlocks);
+}
+
+}  // namespace
+
+bool b200_conv_stem_supported(int c0, int c1, int cout) { return c0 == 1 && c1 == 0 && (cout == 16 || cout == 32 || cout == 8); }
+bool b200_conv_stem_wgrad_supported(int c0, int c1, int cout) { return c0 == 1 && c1 == 0 && (cout == 16 || cout == 8); }
+
+int b200_conv_stem_fwd(int dtype, const void* x, const void* wpack, const float* bias, void* y, int cout, int N, int D, int H, int W,
+                       cudaStream_t st) {
+  const int tiles_w = (W + FT_W - 1) / FT_W, tiles_h = (H + FT_H - 1) / FT_H;
+  const int64_t grid = (int64_t)tiles_w * tiles_h * N * D;
+  B200_REQUIRE(grid < 2147483647LL, B200_ERR_UNSUPPORTED, "conv_stem_fwd: volume too large");
+#define RUN(T, C) stem_fwd_kernel<T, C><<<(unsigned)grid, kFwdThreads, 0, st>>>((const T*)x, (const T*)wpack, bias, (T*)y, N, D, H, W, tiles_w, tiles_h)
+  if (dtype == B200_F32) { if (cout == 8) RUN(float, 8); else if (cout == 16) RUN(float, 16); else RUN(float, 32); }
+  else { if (cout == 8) RUN(__nv_bfloat16, 8); else if (cout == 16) RUN(__nv_bfloat16, 16); else RUN(__nv_bfloat16, 32); }
+#undef RUN
+  B200_CHECK_LAUNCH("conv_stem_fwd");
+  return B200_OK;
+}
+
+int64_t b200_conv_stem_wgrad_workspace(int cout) { return (int64_t)kWgMaxBlocks * 27 * cout * 4; }
+
+int b200_conv_stem_wgrad(int dtype, const void* x, const void* dy, int cout, float* dw, float* partials, int N, int D, int H, int W,
+                         cudaStream_t st) {
+  const int tiles_w = (W + WT - 1) / WT, tiles_h = (H + WT - 1) / WT, tiles_d = (D + WT - 1) / WT;
+  const int nblocks = wg_blocks(N, D, H, W);
+#define RUN(T, C) stem_wgrad_kernel<T, C><<<nblocks, 8 * 9 * (C / 4), 0, st>>>((const T*)x, (const T*)dy, partials, N, D, H, W, tiles_w, tiles_h, tiles_d)
+  if (dtype == B200_F32) { if (cout == 8) RUN(float, 8); else RUN(float, 16); }
+  else { if (cout == 8) RUN(__nv_bfloat16, 8); else RUN(__nv_bfloat16, 16); }
+#undef RUN
+  B200_CHECK_LAUNCH("conv_stem_wgrad");
+  stem_wgrad_finalize_kernel<<<(27 * cout * 32 + 127) / 128, 128, 0, st>>>(partials, nblocks, cout, dw);
+  B200_CHECK_LAUNCH("conv_stem_wgrad_finalize");
+  return B200_OK;
+}

@@ -118,22 +118,28 @@ bn_stats_kernel(const T* __restrict__ x, int64_t M, int C, float* __restrict__ p
       M, C, partials);
 }
 
+// Sums partials[b][slot][c] over b with one WARP per channel: lane l takes blocks l, l+32, ... in fp64,
+// then a fixed-shape butterfly — deterministic, and ~30x shorter than a serial loop over 592 blocks.
+__device__ __forceinline__ double warp_block_sum(const float* __restrict__ partials, int nblocks, int C, int slot, int c, int lane) {
+  double s = 0.0;
+  for (int b = lane; b < nblocks; b += 32) s += (double)partials[(int64_t)b * 2 * C + slot * C + c];
+  return warp_sum_d(s);
+}
+
 __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nblocks, int64_t M, int C,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, int training, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, int64_t* __restrict__ nbt,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && training && nbt) nbt[0] += 1;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c == 0 && lane == 0 && training && nbt) nbt[0] += 1;
   if (c >= C) return;
   float mean, var;
   if (training) {
-    double s = 0.0, ss = 0.0;
-    for (int b = 0; b < nblocks; ++b) {
-      s += (double)partials[(int64_t)b * 2 * C + c];
-      ss += (double)partials[(int64_t)b * 2 * C + C + c];
-    }
+    const double s = warp_block_sum(partials, nblocks, C, 0, c, lane);
+    const double ss = warp_block_sum(partials, nblocks, C, 1, c, lane);
+    if (lane != 0) return;
     const double m = s / (double)M;
     double v = ss / (double)M - m * m;
     if (v < 0.0) v = 0.0;
@@ -145,6 +151,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nbloc
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
     }
   } else {
+    if (lane != 0) return;
     mean = running_mean[c];
     var = running_var[c];
   }
@@ -232,13 +239,11 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ gy, const T* __restrict__ x, cons
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int64_t M, int C,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ sums) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    s += (double)partials[(int64_t)b * 2 * C + c];
-    ss += (double)partials[(int64_t)b * 2 * C + C + c];
-  }
+  const double s = warp_block_sum(partials, nblocks, C, 0, c, lane);
+  const double ss = warp_block_sum(partials, nblocks, C, 1, c, lane);
+  if (lane != 0) return;
   if (dbeta) dbeta[c] = (float)s;
   if (dgamma) dgamma[c] = (float)ss;
   sums[c] = (float)(s / (double)M);
@@ -287,11 +292,10 @@ channel_sum_kernel(const T* __restrict__ x, int64_t M, int C, float* __restrict_
       M, C, partials);
 }
 __global__ void channel_sum_finalize_kernel(const float* __restrict__ partials, int nblocks, int C, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
-  double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += (double)partials[(int64_t)b * 2 * C + c];
-  out[c] = (float)s;
+  const double s = warp_block_sum(partials, nblocks, C, 0, c, lane);
+  if (lane == 0) out[c] = (float)s;
 }
 
 // ------------------------------------------------------------------ MaxPool3d(2,2)
@@ -620,7 +624,7 @@ extern "C" int b200_bn_finalize(const float* partials, int64_t M, int C, const f
   B200_REQUIRE(training ? partials != nullptr : (running_mean && running_var), B200_ERR_SHAPE,
                "bn_finalize: %s", training ? "partials required in training mode" : "running stats required in eval mode");
   const RowMap rm = row_map(M, C);
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, rm.nblocks, M, C, gamma, beta, eps, momentum,
+  bn_finalize_kernel<<<(C * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, rm.nblocks, M, C, gamma, beta, eps, momentum,
                                                                      training, running_mean, running_var,
                                                                      num_batches_tracked, scale, shift, mean, invstd);
   B200_CHECK_LAUNCH("bn_finalize");
@@ -658,7 +662,7 @@ extern "C" int b200_bn_bwd_finalize(const float* partials, int64_t M, int C, flo
   if (rc) return rc;
   B200_REQUIRE(partials && sums, B200_ERR_SHAPE, "bn_bwd_finalize: null pointer");
   const RowMap rm = row_map(M, C);
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, rm.nblocks, M, C, dgamma, dbeta, sums);
+  bn_bwd_finalize_kernel<<<(C * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, rm.nblocks, M, C, dgamma, dbeta, sums);
   B200_CHECK_LAUNCH("bn_bwd_finalize");
   return B200_OK;
 }
@@ -684,7 +688,7 @@ extern "C" int b200_channel_sum(int dtype, const void* x, int64_t M, int C, floa
   const size_t smem = (size_t)rm.rows_per_iter * 2 * C * sizeof(float);
   B200_DISPATCH_DTYPE(dtype, T, (channel_sum_kernel<T><<<rm.nblocks, kThreads, smem, (cudaStream_t)stream>>>((const T*)x, M, C, partials)));
   B200_CHECK_LAUNCH("channel_sum");
-  channel_sum_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, rm.nblocks, C, out);
+  channel_sum_finalize_kernel<<<(C * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, rm.nblocks, C, out);
   B200_CHECK_LAUNCH("channel_sum_finalize");
   return B200_OK;
 }

@@ -136,10 +136,12 @@ conv1x1_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const f
 __global__ void conv1x1_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int Cin, int Cout,
                                             float* __restrict__ dw, float* __restrict__ db) {
   const int Cin1 = Cin + 1, P = Cout * Cin1;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (p >= P) return;
   double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += (double)partials[(int64_t)b * P + p];
+  for (int b = lane; b < nblocks; b += 32) s += (double)partials[(int64_t)b * P + p];
+  s = warp_sum_d(s);
+  if (lane != 0) return;
   const int co = p / Cin1, ci = p % Cin1;
   if (ci < Cin) { if (dw) dw[co * Cin + ci] = (float)s; }
   else if (db) db[co] = (float)s;
@@ -266,7 +268,7 @@ extern "C" int b200_conv1x1_bwd(int dtype, const void* x, const float* w, const 
   }
   B200_CHECK_LAUNCH("conv1x1_bwd");
   if (dw || db) {
-    conv1x1_bwd_finalize_kernel<<<(P + 127) / 128, 128, 0, st>>>(partials, nblocks, Cin, Cout, dw, db);
+    conv1x1_bwd_finalize_kernel<<<(P * 32 + 127) / 128, 128, 0, st>>>(partials, nblocks, Cin, Cout, dw, db);
     B200_CHECK_LAUNCH("conv1x1_bwd_finalize");
   }
   return B200_OK;

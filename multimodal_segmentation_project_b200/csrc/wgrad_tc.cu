@@ -200,23 +200,25 @@ wgrad_tc_kernel(const WgParams g) {
         }
         tc::tc_fence_after();
         const uint32_t q_base = tc::smem_u32(qbuf + qst * kQBytes);
+        // r outermost: consecutive MMAs go to different accumulators (no back-to-back dependent chain)
+        for (int r = 0; r < 16; ++r) {
+#pragma unroll
+          for (int kd = 0; kd < 3; ++kd) {
+            const int pl = q - kd + 1;
+            if (pl < 0 || pl >= planes) continue;
+            const uint64_t adesc = desc_mn_sw32(tc::smem_u32(pbuf + (pl % kPStages) * p_stage_bytes) + r * 512, a_lbo, 256);
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              const uint64_t bdesc = desc_mn_sw32(q_base + (r + kh) * (kQPitch * 32), 32, 256);
+              const uint32_t acc = (r > 0) ? 1u : ((touched >> (kd * 3 + kh)) & 1u);
+              tc::umma_bf16_ss(tmem_base + (uint32_t)((kd * 3 + kh) * 48), adesc, bdesc, idesc, acc);
+            }
+          }
+        }
 #pragma unroll
         for (int kd = 0; kd < 3; ++kd) {
           const int pl = q - kd + 1;
-          if (pl < 0 || pl >= planes) continue;
-          const uint32_t p_base = tc::smem_u32(pbuf + (pl % kPStages) * p_stage_bytes);
-#pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)((kd * 3 + kh) * 48);
-            uint32_t acc = (touched >> (kd * 3 + kh)) & 1u;
-            for (int r = 0; r < 16; ++r) {
-              const uint64_t adesc = desc_mn_sw32(p_base + r * 512, a_lbo, 256);
-              const uint64_t bdesc = desc_mn_sw32(q_base + (r + kh) * (kQPitch * 32), 32, 256);
-              tc::umma_bf16_ss(d_tmem, adesc, bdesc, idesc, acc);
-              acc = 1;
-            }
-            touched |= 1u << (kd * 3 + kh);
-          }
+          if (pl >= 0 && pl < planes) touched |= 7u << (kd * 3);
         }
         tc::umma_commit(q_empty(qst));
         if (q - 1 >= 0 && q - 1 < planes) tc::umma_commit(p_empty((q - 1) % kPStages));  // plane q-1 was last used here (kd = 2)
@@ -257,7 +259,8 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int sp
                                        int swapped, float* __restrict__ dw) {
   const int64_t stride = (int64_t)mrows * 27 * 16;
   const int64_t total = (int64_t)Cout * Cin * 27;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < total; i += ((int64_t)gridDim.x * blockDim.x) >> 5) {
     const int tap = (int)(i % 27);
     const int ci = (int)((i / 27) % Cin);
     const int co = (int)(i / (27 * (int64_t)Cin));
@@ -267,8 +270,9 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int sp
     const int mchunk = m / 64, mm = m % 64, qslab = nn / 16, nl = nn % 16;
     const float* src = partial + (((int64_t)qslab * mchunks + mchunk) * spatial) * stride + ((int64_t)mm * 27 + t) * 16 + nl;
     double s = 0.0;
-    for (int c = 0; c < spatial; ++c) s += (double)src[(int64_t)c * stride];
-    dw[i] = (float)s;
+    for (int c = lane; c < spatial; c += 32) s += (double)src[(int64_t)c * stride];
+    s = warp_sum_d(s);
+    if (lane == 0) dw[i] = (float)s;
   }
 }
 
@@ -338,7 +342,7 @@ int b200_conv3d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const v
   wgrad_tc_kernel<<<grid, kThreads, pl.smem, stream>>>(g);
   B200_CHECK_LAUNCH("conv3d_wgrad_tc");
   const int64_t total = (int64_t)Cout * (c0 + c1) * 27;
-  wgrad_tc_reduce_kernel<<<b200_grid_for(total, 256, B200_NUM_SMS * 8), 256, 0, stream>>>((const float*)workspace, pl.spatial, pl.mchunks, g.mrows,
+  wgrad_tc_reduce_kernel<<<b200_grid_for(total * 32, 256, B200_NUM_SMS * 16), 256, 0, stream>>>((const float*)workspace, pl.spatial, pl.mchunks, g.mrows,
                                                                                         Cout, c0 + c1, pl.swapped, dw);
   B200_CHECK_LAUNCH("conv3d_wgrad_tc_reduce");
   return B200_OK;
