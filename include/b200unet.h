@@ -109,15 +109,16 @@ int b200_conv3d_wgrad(int dtype, const void* x0, int c0, const void* x1, int c1,
 
 /* ---------------------------------------------------------------- BatchNorm3d + ReLU + Dropout3d
  * models/unet.py:12-14,16-18.  Statistics are per channel over M = N*D*H*W rows.
- * bn_stats writes per-block partial sums to `partials` (b200_bn_partials_bytes(C) bytes, fp32),
- * bn_finalize reduces them in fixed order in fp64 -> deterministic.
+ * bn_stats writes per-block partial sums of (x - x[row 0]) and (x - x[row 0])^2 to `partials`
+ * (b200_bn_partials_bytes(C) bytes, fp32; the shift avoids cancellation when |mean| >> std),
+ * bn_finalize (given the same x) reduces them in fixed order in fp64 -> deterministic.
  */
 int64_t b200_bn_partials_bytes(int C);
 int b200_bn_stats(int dtype, const void* x, int64_t M, int C, float* partials, void* stream);
 /* training != 0: batch statistics (biased var for normalisation, unbiased for running_var,
  * momentum update, num_batches_tracked += 1); training == 0: running statistics.
  * Outputs scale[c] = gamma*invstd, shift[c] = beta - mean*scale, mean[c], invstd[c]. */
-int b200_bn_finalize(const float* partials, int64_t M, int C, const float* gamma, const float* beta,
+int b200_bn_finalize(int dtype, const void* x, const float* partials, int64_t M, int C, const float* gamma, const float* beta,
                      float eps, float momentum, int training, float* running_mean, float* running_var,
                      int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* invstd,
                      void* stream);
@@ -191,6 +192,13 @@ int b200_seg_loss_bwd(const float* logits, const float* teacher, const int64_t* 
 int b200_confusion(const float* logits, const int64_t* target, int64_t N, int C, int64_t S, int64_t* conf, void* stream);
 /* argmax mask only: out [N, S] uint8 */
 int b200_argmax(const float* logits, int64_t N, int C, int64_t S, uint8_t* out, void* stream);
+
+/* sliding-window inference (BASELINE config #5; the evaluator test_model.py:248 runs whole volumes):
+ * acc[c, d0+z, h0+y, w0+x] += logits[c, z, y, x], cnt[d0+z, h0+y, w0+x] += 1 for one window;
+ * finalize divides acc by cnt (voxels never covered stay 0). acc [C,D,H,W] fp32, cnt [D,H,W] fp32. */
+int b200_window_accumulate(float* acc, float* cnt, const float* logits, int C, int D, int H, int W,
+                           int d0, int h0, int w0, int wd, int wh, int ww, void* stream);
+int b200_window_finalize(float* acc, const float* cnt, int C, int64_t S, void* stream);
 
 /* ---------------------------------------------------------------- DANN  models/unet_dann.py:79, train_dann.py:22-49 */
 /* torch.mean(bottleneck, dim=[2,3,4]): x NDHWC [N,S,C] -> out fp32 [N,C]; and its adjoint */

@@ -54,7 +54,7 @@ def _declare(lib) -> None:
         "b200_conv3d_wgrad": (I, [I, P, I, P, I, P, I, P, P, P, L, I, I, I, I, P]),
         "b200_bn_partials_bytes": (L, [I]),
         "b200_bn_stats": (I, [I, P, L, I, P, P]),
-        "b200_bn_finalize": (I, [P, L, I, P, P, F, F, I, P, P, P, P, P, P, P, P]),
+        "b200_bn_finalize": (I, [I, P, P, L, I, P, P, F, F, I, P, P, P, P, P, P, P, P]),
         "b200_bn_act_fwd": (I, [I, P, P, P, P, P, I, L, L, I, P]),
         "b200_bn_act_bwd_reduce": (I, [I, P, P, P, P, P, P, P, I, L, L, I, P, P]),
         "b200_bn_bwd_finalize": (I, [P, L, I, P, P, P, P]),
@@ -77,6 +77,8 @@ def _declare(lib) -> None:
         "b200_seg_loss_bwd": (I, [P, P, P, P, P, F, L, I, L, P, P]),
         "b200_confusion": (I, [P, P, L, I, L, P, P]),
         "b200_argmax": (I, [P, L, I, L, P, P]),
+        "b200_window_accumulate": (I, [P, P, P, I, I, I, I, I, I, I, I, I, I, P]),
+        "b200_window_finalize": (I, [P, P, I, L, P]),
         "b200_gap_fwd": (I, [I, P, P, L, L, I, P]),
         "b200_gap_bwd": (I, [I, P, P, I, L, L, I, P]),
         "b200_scale_f32": (I, [P, P, F, L, P]),

@@ -106,6 +106,15 @@ __device__ __forceinline__ void block_channel_reduce(F&& body, int64_t M, int C,
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 bn_stats_kernel(const T* __restrict__ x, int64_t M, int C, float* __restrict__ partials) {
+  // shifted sums: K[c] = x[row 0][c] is subtracted before accumulating, so that
+  // var = E[(x-K)^2] - E[x-K]^2 does not cancel catastrophically when |mean| >> std
+  const int cvk = threadIdx.x % (C / 8);
+  float k[8];
+  {
+    Vec8<T> v0;
+    v0.load(x + cvk * 8);
+    v0.get(k);
+  }
   block_channel_reduce(
       [&](int64_t row, int cv, float (&a0)[8], float (&a1)[8]) {
         Vec8<T> v;
@@ -113,7 +122,7 @@ bn_stats_kernel(const T* __restrict__ x, int64_t M, int C, float* __restrict__ p
         float f[8];
         v.get(f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { a0[i] += f[i]; a1[i] = fmaf(f[i], f[i], a1[i]); }
+        for (int i = 0; i < 8; ++i) { const float d = f[i] - k[i]; a0[i] += d; a1[i] = fmaf(d, d, a1[i]); }
       },
       M, C, partials);
 }
@@ -126,7 +135,8 @@ __device__ __forceinline__ double warp_block_sum(const float* __restrict__ parti
   return warp_sum_d(s);
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nblocks, int64_t M, int C,
+template <typename T>
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, const T* __restrict__ x_row0, int nblocks, int64_t M, int C,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, int training, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, int64_t* __restrict__ nbt,
@@ -140,9 +150,10 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nbloc
     const double s = warp_block_sum(partials, nblocks, C, 0, c, lane);
     const double ss = warp_block_sum(partials, nblocks, C, 1, c, lane);
     if (lane != 0) return;
-    const double m = s / (double)M;
-    double v = ss / (double)M - m * m;
+    const double ms = s / (double)M;  // mean of the shifted values
+    double v = ss / (double)M - ms * ms;
     if (v < 0.0) v = 0.0;
+    const double m = ms + (x_row0 ? (double)to_f32<T>(x_row0[c]) : 0.0);
     mean = (float)m;
     var = (float)v;
     if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
@@ -614,8 +625,8 @@ extern "C" int b200_bn_stats(int dtype, const void* x, int64_t M, int C, float* 
   return B200_OK;
 }
 
-extern "C" int b200_bn_finalize(const float* partials, int64_t M, int C, const float* gamma, const float* beta, float eps,
-                                float momentum, int training, float* running_mean, float* running_var,
+extern "C" int b200_bn_finalize(int dtype, const void* x, const float* partials, int64_t M, int C, const float* gamma, const float* beta,
+                                float eps, float momentum, int training, float* running_mean, float* running_var,
                                 int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* invstd,
                                 void* stream) {
   int rc = check_rows("bn_finalize", M, C);
@@ -624,9 +635,10 @@ extern "C" int b200_bn_finalize(const float* partials, int64_t M, int C, const f
   B200_REQUIRE(training ? partials != nullptr : (running_mean && running_var), B200_ERR_SHAPE,
                "bn_finalize: %s", training ? "partials required in training mode" : "running stats required in eval mode");
   const RowMap rm = row_map(M, C);
-  bn_finalize_kernel<<<(C * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, rm.nblocks, M, C, gamma, beta, eps, momentum,
-                                                                     training, running_mean, running_var,
-                                                                     num_batches_tracked, scale, shift, mean, invstd);
+  B200_REQUIRE(!training || x != nullptr, B200_ERR_SHAPE, "bn_finalize: x (the tensor bn_stats ran on) is required in training mode");
+  B200_DISPATCH_DTYPE(dtype, T, (bn_finalize_kernel<T><<<(C * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+                                    partials, (const T*)x, rm.nblocks, M, C, gamma, beta, eps, momentum, training, running_mean, running_var,
+                                    num_batches_tracked, scale, shift, mean, invstd)));
   B200_CHECK_LAUNCH("bn_finalize");
   return B200_OK;
 }

@@ -129,7 +129,45 @@ argmax_kernel(const float* __restrict__ logits, int64_t N, int C, int64_t S, uin
   }
 }
 
+__global__ void window_accumulate_kernel(float* __restrict__ acc, float* __restrict__ cnt, const float* __restrict__ logits, int C,
+                                         int D, int H, int W, int d0, int h0, int w0, int wd, int wh, int ww) {
+  const int64_t wvox = (int64_t)wd * wh * ww;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < wvox; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % ww), y = (int)((i / ww) % wh), z = (int)(i / ((int64_t)ww * wh));
+    const int64_t dst = ((int64_t)(d0 + z) * H + (h0 + y)) * W + (w0 + x);
+    for (int c = 0; c < C; ++c) acc[(int64_t)c * D * H * W + dst] += logits[(int64_t)c * wvox + i];
+    cnt[dst] += 1.f;
+  }
+}
+__global__ void window_finalize_kernel(float* __restrict__ acc, const float* __restrict__ cnt, int C, int64_t S) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < S; i += (int64_t)gridDim.x * blockDim.x) {
+    const float n = cnt[i];
+    if (n > 1.f) {
+      const float inv = 1.f / n;
+      for (int c = 0; c < C; ++c) acc[(int64_t)c * S + i] *= inv;
+    }
+  }
+}
+
 }  // namespace
+
+extern "C" int b200_window_accumulate(float* acc, float* cnt, const float* logits, int C, int D, int H, int W, int d0, int h0, int w0,
+                                      int wd, int wh, int ww, void* stream) {
+  B200_REQUIRE(acc && cnt && logits, B200_ERR_SHAPE, "window_accumulate: null pointer");
+  B200_REQUIRE(C > 0 && wd > 0 && wh > 0 && ww > 0 && d0 >= 0 && h0 >= 0 && w0 >= 0 && d0 + wd <= D && h0 + wh <= H && w0 + ww <= W,
+               B200_ERR_SHAPE, "window_accumulate: window [%d,%d,%d]+[%d,%d,%d] outside volume [%d,%d,%d]", d0, h0, w0, wd, wh, ww, D, H, W);
+  const int64_t wvox = (int64_t)wd * wh * ww;
+  window_accumulate_kernel<<<b200_grid_for(wvox, kThreads, B200_NUM_SMS * 8), kThreads, 0, (cudaStream_t)stream>>>(acc, cnt, logits, C, D, H, W,
+                                                                                                                 d0, h0, w0, wd, wh, ww);
+  B200_CHECK_LAUNCH("window_accumulate");
+  return B200_OK;
+}
+extern "C" int b200_window_finalize(float* acc, const float* cnt, int C, int64_t S, void* stream) {
+  B200_REQUIRE(acc && cnt && C > 0 && S > 0, B200_ERR_SHAPE, "window_finalize: bad arguments");
+  window_finalize_kernel<<<b200_grid_for(S, kThreads, B200_NUM_SMS * 8), kThreads, 0, (cudaStream_t)stream>>>(acc, cnt, C, S);
+  B200_CHECK_LAUNCH("window_finalize");
+  return B200_OK;
+}
 
 extern "C" int b200_confusion(const float* logits, const int64_t* target, int64_t N, int C, int64_t S, int64_t* conf,
                               void* stream) {

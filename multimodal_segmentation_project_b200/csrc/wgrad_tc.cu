@@ -18,6 +18,7 @@
 //     dW to a workspace; a second kernel reduces the partials in fixed order (deterministic).
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -40,6 +41,7 @@ struct WgParams {
   int N, D, H, W;
   int mslabs;                   // 16-channel slabs of P handled per CTA (1..4)
   int dseg, dblocks, tiles_w, tiles_h;
+  int m128;                     // issue M=128 MMAs (rows beyond the real channels are ignored)
 };
 
 __device__ __forceinline__ uint32_t swz32(uint32_t off) { return off ^ (((off >> 7) & 1u) << 4); }
@@ -185,7 +187,7 @@ wgrad_tc_kernel(const WgParams g) {
     // ===================== MMA issue =====================
     if (lane == 0) {
       // M = 64, N = 48, A and B MN-major
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((48u >> 3) << 17) | ((64u >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((48u >> 3) << 17) | ((g.m128 ? (128u >> 4) : (64u >> 4)) << 24);
       const uint32_t a_lbo = g.mslabs > 1 ? kPSlabBytes : 0;   // M-group (16 ch) stride; rows beyond the real channels are ignored
       uint32_t touched = 0;
       int p_ready = 0;  // number of P planes whose full-barrier has been observed
@@ -200,25 +202,23 @@ wgrad_tc_kernel(const WgParams g) {
         }
         tc::tc_fence_after();
         const uint32_t q_base = tc::smem_u32(qbuf + qst * kQBytes);
-        // r outermost: consecutive MMAs go to different accumulators (no back-to-back dependent chain)
-        for (int r = 0; r < 16; ++r) {
-#pragma unroll
-          for (int kd = 0; kd < 3; ++kd) {
-            const int pl = q - kd + 1;
-            if (pl < 0 || pl >= planes) continue;
-            const uint64_t adesc = desc_mn_sw32(tc::smem_u32(pbuf + (pl % kPStages) * p_stage_bytes) + r * 512, a_lbo, 256);
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-              const uint64_t bdesc = desc_mn_sw32(q_base + (r + kh) * (kQPitch * 32), 32, 256);
-              const uint32_t acc = (r > 0) ? 1u : ((touched >> (kd * 3 + kh)) & 1u);
-              tc::umma_bf16_ss(tmem_base + (uint32_t)((kd * 3 + kh) * 48), adesc, bdesc, idesc, acc);
-            }
-          }
-        }
 #pragma unroll
         for (int kd = 0; kd < 3; ++kd) {
           const int pl = q - kd + 1;
-          if (pl >= 0 && pl < planes) touched |= 7u << (kd * 3);
+          if (pl < 0 || pl >= planes) continue;
+          const uint32_t p_base = tc::smem_u32(pbuf + (pl % kPStages) * p_stage_bytes);
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)((kd * 3 + kh) * 48);
+            uint32_t acc = (touched >> (kd * 3 + kh)) & 1u;
+            for (int r = 0; r < 16; ++r) {
+              const uint64_t adesc = desc_mn_sw32(p_base + r * 512, a_lbo, 256);
+              const uint64_t bdesc = desc_mn_sw32(q_base + (r + kh) * (kQPitch * 32), 32, 256);
+              tc::umma_bf16_ss(d_tmem, adesc, bdesc, idesc, acc);
+              acc = 1;
+            }
+            touched |= 1u << (kd * 3 + kh);
+          }
         }
         tc::umma_commit(q_empty(qst));
         if (q - 1 >= 0 && q - 1 < planes) tc::umma_commit(p_empty((q - 1) % kPStages));  // plane q-1 was last used here (kd = 2)
@@ -231,7 +231,9 @@ wgrad_tc_kernel(const WgParams g) {
     tc::mbar_wait(acc_done, 0);
     tc::tc_fence_after();
     const int m_real = min(64, g.cp - mchunk * 64);
-    const int co = ew * 16 + lane;  // M=64 accumulators: row m lives in TMEM lane (m % 16) + 32 * (m / 16)
+    // M=64 accumulators: row m lives in TMEM lane (m % 16) + 32 * (m / 16); M=128: row m = lane m
+    const int co = g.m128 ? ew * 32 + lane : ew * 16 + lane;
+    const bool row_ok = (g.m128 || lane < 16) && co < m_real;
     const int64_t cta = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     float* out = g.partial + cta * (int64_t)(g.mrows * 27 * 16);
     for (int t9 = 0; t9 < 9; ++t9) {
@@ -240,7 +242,7 @@ wgrad_tc_kernel(const WgParams g) {
         uint32_t r[16];
         tc::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(t9 * 48 + kw * 16), r);
         tc::tmem_ld_wait();
-        if (lane < 16 && co < m_real) {
+        if (row_ok) {
           float4* dst = reinterpret_cast<float4*>(out + ((int64_t)co * 27 + t9 * 3 + kw) * 16);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
@@ -331,6 +333,10 @@ int b200_conv3d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const v
   g.partial = (float*)workspace;
   g.mrows = pl.cp < 64 ? pl.cp : 64;
   g.N = N; g.D = D; g.H = H; g.W = W;
+  {
+    const char* e = getenv("B200_WGRAD_M128");
+    g.m128 = e ? atoi(e) : 0;
+  }
   g.mslabs = pl.mslabs; g.dseg = pl.dseg; g.dblocks = pl.dblocks; g.tiles_w = pl.tiles_w; g.tiles_h = pl.tiles_h;
   static bool attr_set = false;
   if (!attr_set) {

@@ -191,7 +191,7 @@ class _ConvBNAct(torch.autograd.Function):
             check(L.b200_bn_stats(_dt(conv_out), _ptr(conv_out), M, Cout, _ptr(partials), _stream()), "bn_stats")
         g32, b32 = _f32(gamma), _f32(beta)
         check(
-            L.b200_bn_finalize(_ptr(partials), M, Cout, _ptr(g32), _ptr(b32), float(eps), float(momentum), int(training),
+            L.b200_bn_finalize(_dt(conv_out), _ptr(conv_out), _ptr(partials), M, Cout, _ptr(g32), _ptr(b32), float(eps), float(momentum), int(training),
                                _ptr(running_mean), _ptr(running_var), _ptr(nbt), _ptr(stats[0]), _ptr(stats[1]),
                                _ptr(stats[2]), _ptr(stats[3]), _stream()),
             "bn_finalize",
