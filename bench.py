@@ -318,12 +318,18 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
+    # Leave without tearing NCCL down: destroy_process_group() can dead-lock while a captured CUDA graph still
+    # references the communicator (observed on 2 GPUs: JSON printed, then the job hung until the time limit).
+    sys.stdout.flush()
+    sys.stderr.flush()
     try:
         import torch.distributed as dist
         if dist.is_initialized():
-            dist.destroy_process_group()
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            os._exit(0)
     except Exception:
-        pass
+        os._exit(0)
 
 
 if __name__ == "__main__":
