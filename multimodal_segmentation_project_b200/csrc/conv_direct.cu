@@ -14,6 +14,7 @@
 //   rows_gemm : C[m, n] = sum_k A(m, k) B(k, n),  m = voxel rows (large), A gathered
 //   cols_gemm : C[r, c] = sum_v A(v, r) B(v, c),  v = voxel rows (reduction, split over CTAs)
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -506,6 +507,15 @@ int b200_conv3d_k3_tc(const void* x0, int c0, const void* x1, int c1, const void
 int b200_pack_conv3_weights_tc(int mode, const float* w, void* out, int Cout, int Cin, cudaStream_t stream);
 int64_t b200_pack_conv3_bytes_tc(int Cout, int Cin);
 bool b200_conv3d_k3_tc_supported(int c0, int c1, int co0, int co1, int N, int D, int H, int W);
+// second-generation tcgen05 path (conv_tc2.cu): TMA-fed stages, kd-fused MMAs
+int b200_conv3d_k3_tc2(const void* x0, int c0, const void* x1, int c1, const void* wpack, const float* bias, void* y0,
+                       int co0, void* y1, int co1, int N, int D, int H, int W, cudaStream_t stream);
+int b200_pack_conv3_weights_tc2(int mode, const float* w, void* out, int Cout, int Cin, cudaStream_t stream);
+static int tc_version() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200_CONV_TC_VERSION"); v = e ? atoi(e) : 2; }
+  return v;
+}
 // tcgen05 weight gradient (wgrad_tc.cu)
 bool b200_conv3d_wgrad_tc_supported(int c0, int c1, int Cout, int N, int D, int H, int W);
 int64_t b200_conv3d_wgrad_tc_workspace(int c0, int c1, int Cout, int N, int D, int H, int W);
@@ -531,6 +541,7 @@ extern "C" int b200_pack_conv3_weights(int mode, int dtype, const float* w, void
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == B200_PACK_FPROP_TC || mode == B200_PACK_DGRAD_TC) {
     B200_REQUIRE(dtype == B200_BF16, B200_ERR_UNSUPPORTED, "pack_conv3_weights: tcgen05 layouts are bf16 only");
+    if (tc_version() == 2) return b200_pack_conv3_weights_tc2(mode, w, out, Cout, Cin, st);
     return b200_pack_conv3_weights_tc(mode, w, out, Cout, Cin, st);
   }
   B200_REQUIRE(mode == B200_PACK_FPROP || mode == B200_PACK_DGRAD, B200_ERR_UNSUPPORTED, "pack_conv3_weights: mode %d", mode);
@@ -558,6 +569,9 @@ extern "C" int b200_conv3d_k3(int dtype, int impl, const void* x0, int c0, const
                "conv3d_k3: impl must be 1 (CUDA-core) or 2 (tcgen05); resolve 0 with b200_conv3d_k3_select so that the weights are packed to match");
   if (impl == 2) {
     B200_REQUIRE(dtype == B200_BF16, B200_ERR_UNSUPPORTED, "conv3d_k3: tcgen05 path is bf16 only");
+    B200_REQUIRE(b200_conv3d_k3_tc_supported(c0, c1, co0, co1, N, D, H, W), B200_ERR_UNSUPPORTED,
+                 "conv3d_k3(tcgen05): channels (%d+%d)->(%d+%d) need multiples of 16 (Cout <= 128 or a multiple of 128)", c0, c1, co0, co1);
+    if (tc_version() == 2) return b200_conv3d_k3_tc2(x0, c0, x1, c1, wpack, bias, y0, co0, y1, co1, N, D, H, W, st);
     return b200_conv3d_k3_tc(x0, c0, x1, c1, wpack, bias, y0, co0, y1, co1, N, D, H, W, st);
   }
   if (co1 == 0 && b200_conv_stem_supported(c0, c1, co0) && (dtype == B200_F32 || dtype == B200_BF16))

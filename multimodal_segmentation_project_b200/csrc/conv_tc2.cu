@@ -1,0 +1,346 @@
+// conv_tc2.cu — second generation of the tcgen05 / TMEM implicit-GEMM 3x3x3 convolution
+// (bf16 in, fp32 accumulate in TMEM, bf16 out).  Same plane-streaming formulation as conv_tc.cu, plus:
+//
+//   * TMA-fed stages: every (d-plane, 16-channel slab) halo plane is fetched by ONE
+//     cp.async.bulk.tensor.5d copy (box 16 ch x 18 x 18) from a SWIZZLE_32B tensor map over the NDHWC
+//     activation into [voxel][16 ch] rows of 32 bytes — the K-major SWIZZLE_32B UMMA layout, in which a
+//     filter tap (kh,kw) is still just a byte offset of the descriptor start (the swizzle is a function
+//     of the absolute shared-memory address, so unaligned 32-byte shifts stay consistent with what TMA
+//     wrote).  Out-of-volume coordinates are zero-filled by the TMA unit (that IS the conv padding);
+//     completion is signalled on the stage's mbarrier — no producer warps, no registers.
+//   * kd-fused MMAs: for a staged input plane and a tap (kh,kw) the A operand (the shifted 128-voxel
+//     view) is the same for kd = 0,1,2 — only the output plane differs.  Accumulators of consecutive
+//     planes sit in consecutive TMEM columns (descending plane order) and the packed weights keep the
+//     three kd blocks adjacent, so ONE tcgen05.mma with N = 3*Cout covers three taps: the 4 KB A tile
+//     is read from shared memory once instead of three times (the measured limiter of v1 for
+//     Cout <= 32, see profiles/r01_ncu_conv_wgrad_summary.md).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include <cuda.h>
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int kHalo = 18;
+constexpr int kPlaneVox = kHalo * kHalo;            // 324
+constexpr int kStageBytes = 10496;                  // 324 voxels x 32 B = 10368, rounded up to the 256-byte SWIZZLE_32B period
+constexpr int kStageTx = kPlaneVox * 32;            // bytes written per stage by one TMA box
+constexpr int kMaxStages = 6;
+constexpr int kThreads = 256;                       // w0: act TMA, w1: weight TMA + TMEM alloc, w2: MMA, w4-7: epilogue
+constexpr int kMaxDseg = 8;
+constexpr int kSmemHeader = 512;
+
+struct Tc2Params {
+  const uint8_t* wpack; const float* bias;
+  bf16* y0; bf16* y1; int co0, co1;
+  int c0, c1;
+  int N, D, H, W;
+  int n_tile, dseg, dblocks, slabs, wstages, tmem_cols, tiles_w, stages;
+  int kd_per_mma;   // 3 when 3*n_tile <= 256, else 2 (n_tile = 128)
+};
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, int c, int w, int h, int d, int n, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c), "r"(w), "r"(h), "r"(d), "r"(n), "r"(bar)
+      : "memory");
+}
+// K-major SWIZZLE_32B operand: rows of 32 bytes (16 bf16 = one UMMA K step), 8-row groups SBO bytes apart
+__device__ __forceinline__ uint64_t desc_kmajor_sw32(uint32_t addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                               // LBO: unused for a single swizzled K block
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                               // version
+  d |= (uint64_t)6 << 61;                               // SWIZZLE_32B
+  return d;
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3d_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  // barrier slots: [0,6) a_full, [6,12) a_empty, [12,14) w_full, [14,16) w_empty, [16,24) acc_full
+  const uint32_t bar0 = tc::smem_u32(bars);
+  auto a_full = [&](int i) { return bar0 + 8u * i; };
+  auto a_empty = [&](int i) { return bar0 + 8u * (6 + i); };
+  auto w_full = [&](int i) { return bar0 + 8u * (12 + i); };
+  auto w_empty = [&](int i) { return bar0 + 8u * (14 + i); };
+  auto acc_full = [&](int i) { return bar0 + 8u * (16 + i); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+  uint8_t* act = smem + kSmemHeader;
+  uint8_t* wts = act + p.stages * kStageBytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tw = blockIdx.x % p.tiles_w, th = blockIdx.x / p.tiles_w;
+  const int n = blockIdx.y / p.dblocks, db = blockIdx.y % p.dblocks;
+  const int nchunk = blockIdx.z;
+  const int w0 = tw * 16, h0 = th * 16, d0 = db * p.dseg;
+  const int planes = min(p.dseg, p.D - d0);
+  const int nq = planes + 2;
+  const int total_stages = p.slabs * nq;
+  const uint32_t wbytes = 864u * p.n_tile;
+
+  if (warp == 2 && lane == 0) {
+    for (int i = 0; i < kMaxStages; ++i) { tc::mbar_init(a_full(i), 1); tc::mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(w_full(i), 1); tc::mbar_init(w_empty(i), 1); }
+    for (int i = 0; i < kMaxDseg; ++i) tc::mbar_init(acc_full(i), 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tc::smem_u32(tmem_slot), p.tmem_cols);
+    tc::tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm0);
+    if (p.c1) prefetch_tmap(&tm1);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== activation stages by TMA =====================
+    if (lane == 0) {
+      for (int it = 0; it < total_stages; ++it) {
+        const int s = it / nq, q = it % nq - 1;
+        const int st = it % p.stages;
+        tc::mbar_wait(a_empty(st), ((it / p.stages) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(a_full(st), kStageTx);
+        const int c = s * 16;
+        const CUtensorMap* tm = c < p.c0 ? &tm0 : &tm1;
+        const int cc = c < p.c0 ? c : c - p.c0;
+        const uint32_t dst = tc::smem_u32(act + st * kStageBytes);
+        tma_load_5d(dst, tm, cc, w0 - 1, h0 - 1, d0 + q, n, a_full(st));
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== weight slabs by TMA bulk copy =====================
+    if (lane == 0) {
+      for (int s = 0; s < p.slabs; ++s) {
+        const int ws = s % p.wstages;
+        tc::mbar_wait(w_empty(ws), ((s / p.wstages) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(w_full(ws), wbytes);
+        tc::bulk_g2s(tc::smem_u32(wts + (size_t)ws * wbytes), p.wpack + ((size_t)nchunk * p.slabs + s) * wbytes, wbytes, w_full(ws));
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== MMA issue =====================
+    if (lane == 0) {
+      const uint32_t n_t = p.n_tile;
+      const uint32_t b_lbo = 48u * n_t;        // K-chunk stride of one (kh,kw) B matrix: 3*n rows x 16 B
+      const uint32_t b_tap = 96u * n_t;        // bytes per (kh,kw): 2 chunks x 3*n rows x 16 B
+      for (int s = 0; s < p.slabs; ++s) {
+        const int ws = s % p.wstages;
+        tc::mbar_wait(w_full(ws), (s / p.wstages) & 1);
+        tc::tc_fence_after();
+        const uint32_t w_base = tc::smem_u32(wts + (size_t)ws * wbytes);
+        for (int qi = 0; qi < nq; ++qi) {
+          const int it = s * nq + qi;
+          const int st = it % p.stages;
+          tc::mbar_wait(a_full(st), (it / p.stages) & 1);
+          tc::tc_fence_after();
+          const int q = qi - 1;
+          const uint32_t a_base = tc::smem_u32(act + st * kStageBytes);
+          // valid kd for this input plane: output plane pl = q + 1 - kd in [0, planes)
+          const int kd_lo = max(0, q + 2 - planes), kd_hi = min(2, q + 1);
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const uint32_t a_off = (uint32_t)(kh * kHalo + kw) * 32;
+              const uint32_t b_base = w_base + (uint32_t)(kh * 3 + kw) * b_tap;
+              // kd groups: at the very first contribution of a plane (s == 0, kd == 0, tap (0,0)) the accumulator is
+              // overwritten, so that MMA cannot be fused with planes that already hold partial sums
+              int a = kd_lo;
+              while (a <= kd_hi) {
+                int b = min(kd_hi, a + p.kd_per_mma - 1);
+                uint32_t accumulate = 1;
+                if (s == 0 && kh == 0 && kw == 0 && a == 0) { b = 0; accumulate = 0; }
+                const uint32_t nn = (uint32_t)(b - a + 1) * n_t;
+                const uint32_t idesc = tc::idesc_bf16_f32(128, (int)nn);
+                const uint64_t bdesc = tc::smem_desc_kmajor_noswz(b_base + (uint32_t)a * n_t * 16, b_lbo, 128);
+                // planes q+1-a .. q+1-b occupy ascending column blocks (descending plane order)
+                const uint32_t col = (uint32_t)(p.dseg - 2 - q + a) * n_t;
+#pragma unroll
+                for (int wt = 0; wt < 2; ++wt) {
+                  if (w0 + wt * 8 >= p.W) continue;
+                  const uint64_t adesc = desc_kmajor_sw32(a_base + a_off + wt * 256, kHalo * 32);
+                  tc::umma_bf16_ss(tmem_base + (uint32_t)(wt * p.dseg) * n_t + col, adesc, bdesc, idesc, accumulate);
+                }
+                a = b + 1;
+              }
+            }
+          }
+          tc::umma_commit(a_empty(st));
+          if (s == p.slabs - 1 && q >= 1) tc::umma_commit(acc_full(q - 1));
+        }
+        tc::umma_commit(w_empty(ws));
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;
+    const int m = ew * 32 + lane;
+    const int h = h0 + (m >> 3);
+    for (int pl = 0; pl < planes; ++pl) {
+      tc::mbar_wait(acc_full(pl), 0);
+      tc::tc_fence_after();
+#pragma unroll
+      for (int wt = 0; wt < 2; ++wt) {
+        if (w0 + wt * 8 >= p.W) continue;
+        const int w = w0 + wt * 8 + (m & 7);
+        const bool valid = h < p.H && w < p.W;
+        const int64_t row = (((int64_t)n * p.D + d0 + pl) * p.H + h) * p.W + w;
+        const uint32_t col0 = (uint32_t)((wt * p.dseg + (p.dseg - 1 - pl)) * p.n_tile);
+        for (int cc = 0; cc < p.n_tile / 16; ++cc) {
+          uint32_t r[16];
+          tc::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + col0 + cc * 16, r);
+          tc::tmem_ld_wait();
+          const int ch = nchunk * p.n_tile + cc * 16;
+          uint32_t packed[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float a = __uint_as_float(r[2 * i]), b = __uint_as_float(r[2 * i + 1]);
+            if (p.bias) { a += __ldg(p.bias + ch + 2 * i); b += __ldg(p.bias + ch + 2 * i + 1); }
+            __nv_bfloat162 hb = __floats2bfloat162_rn(a, b);
+            packed[i] = *reinterpret_cast<uint32_t*>(&hb);
+          }
+          if (valid) {
+            bf16* dst = ch < p.co0 ? p.y0 + row * p.co0 + ch : p.y1 + row * p.co1 + (ch - p.co0);
+            reinterpret_cast<uint4*>(dst)[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            reinterpret_cast<uint4*>(dst)[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+          }
+        }
+      }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// out[nchunk][slab][kh][kw][kc(2)][kd(3)][n(n_tile)][8]
+__global__ void pack_k3_tc2_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout_f, int Cin_f, int dgrad, int n_tile, int slabs,
+                                   int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int j = (int)(t % 8); t /= 8;
+    const int nn = (int)(t % n_tile); t /= n_tile;
+    const int kd = (int)(t % 3); t /= 3;
+    const int kc = (int)(t % 2); t /= 2;
+    const int khw = (int)(t % 9); t /= 9;
+    const int slab = (int)(t % slabs);
+    const int nchunk = (int)(t / slabs);
+    const int tap = kd * 9 + khw;
+    const int k = slab * 16 + kc * 8 + j;
+    const int o = nchunk * n_tile + nn;
+    float v;
+    if (!dgrad) v = w[((int64_t)o * Cin_f + k) * 27 + tap];
+    else v = w[((int64_t)k * Cin_f + o) * 27 + (26 - tap)];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+inline int n_tile_for(int cout) { return cout <= 128 ? cout : 128; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// tensor map over an NDHWC bf16 tensor, box = 16 channels x 18 (w) x 18 (h) x 1 x 1, 32-byte swizzle
+int make_act_map(CUtensorMap* tm, const void* base, int C, int N, int D, int H, int W) {
+  EncodeTiledFn enc = get_encode();
+  B200_REQUIRE(enc != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t gstr[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)D * H * W * C * 2};
+  cuuint32_t box[5] = {16, kHalo, kHalo, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for C=%d N=%d D=%d H=%d W=%d", (int)r, C, N, D, H, W);
+  return B200_OK;
+}
+
+}  // namespace
+
+int64_t b200_pack_conv3_bytes_tc2(int Cout, int Cin) { return (int64_t)27 * Cin * Cout * 2; }
+
+int b200_pack_conv3_weights_tc2(int mode, const float* w, void* out, int Cout, int Cin, cudaStream_t stream) {
+  const int dgrad = mode == B200_PACK_DGRAD_TC;
+  const int conv_in = dgrad ? Cout : Cin, conv_out = dgrad ? Cin : Cout;
+  B200_REQUIRE(conv_in % 16 == 0 && conv_out % 16 == 0 && (conv_out <= 128 || conv_out % 128 == 0), B200_ERR_UNSUPPORTED,
+               "pack_conv3_weights(tc2): channel counts %d -> %d not supported by the tcgen05 path", conv_in, conv_out);
+  const int n_tile = n_tile_for(conv_out), slabs = conv_in / 16;
+  const int64_t total = (int64_t)27 * Cin * Cout;
+  pack_k3_tc2_kernel<<<b200_grid_for(total, 256, B200_NUM_SMS * 8), 256, 0, stream>>>(w, (bf16*)out, Cout, Cin, dgrad, n_tile, slabs, total);
+  B200_CHECK_LAUNCH("pack_conv3_weights_tc2");
+  return B200_OK;
+}
+
+int b200_conv3d_k3_tc2(const void* x0, int c0, const void* x1, int c1, const void* wpack, const float* bias, void* y0, int co0, void* y1,
+                       int co1, int N, int D, int H, int W, cudaStream_t stream) {
+  B200_REQUIRE(b200_aligned(x0, 16) && b200_aligned(x1, 16) && b200_aligned(y0, 16) && b200_aligned(y1, 16) && b200_aligned(wpack, 16),
+               B200_ERR_ALIGN, "conv3d_k3(tcgen05): pointers must be 16-byte aligned");
+  Tc2Params p;
+  p.wpack = (const uint8_t*)wpack; p.bias = bias;
+  p.y0 = (bf16*)y0; p.y1 = (bf16*)y1; p.co0 = co0; p.co1 = co1;
+  p.c0 = c0; p.c1 = c1;
+  p.N = N; p.D = D; p.H = H; p.W = W;
+  const int cout = co0 + co1;
+  p.n_tile = n_tile_for(cout);
+  p.slabs = (c0 + c1) / 16;
+  p.kd_per_mma = 3 * p.n_tile <= 256 ? 3 : 2;
+  int dseg = 256 / (2 * p.n_tile);
+  if (dseg > kMaxDseg) dseg = kMaxDseg;
+  if (dseg < 1) dseg = 1;
+  if (dseg > D) dseg = D;
+  p.dseg = dseg;
+  p.dblocks = (D + dseg - 1) / dseg;
+  int cols = dseg * 2 * p.n_tile, pow2 = 32;
+  while (pow2 < cols) pow2 <<= 1;
+  p.tmem_cols = pow2;
+  p.tiles_w = (W + 15) / 16;
+  const int tiles_h = (H + 15) / 16;
+  const size_t wbytes = (size_t)864 * p.n_tile;
+  // shared-memory plan: as many activation stages as fit next to the weight slab(s); keep two CTAs per SM when possible
+  const size_t budget2 = 110 * 1024;  // per CTA for 2 CTAs / SM
+  p.wstages = (p.slabs > 1 && 2 * wbytes + 4 * kStageBytes + kSmemHeader + 1024 <= budget2) ? 2 : 1;
+  size_t avail = (p.wstages * wbytes + 3 * kStageBytes + kSmemHeader + 1024 <= budget2 ? budget2 : (size_t)200 * 1024) - p.wstages * wbytes - kSmemHeader - 1024;
+  int stages = (int)(avail / kStageBytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  B200_REQUIRE(stages >= 2, B200_ERR_UNSUPPORTED, "conv3d_k3(tcgen05): not enough shared memory for n_tile=%d", p.n_tile);
+  p.stages = stages;
+  const size_t smem = kSmemHeader + (size_t)stages * kStageBytes + p.wstages * wbytes + 1024;
+  B200_REQUIRE((int64_t)N * p.dblocks <= 65535 && cout / p.n_tile <= 65535, B200_ERR_UNSUPPORTED, "conv3d_k3(tcgen05): grid too large");
+  CUtensorMap tm0, tm1;
+  int rc = make_act_map(&tm0, x0, c0, N, D, H, W);
+  if (rc) return rc;
+  if (c1) { rc = make_act_map(&tm1, x1, c1, N, D, H, W); if (rc) return rc; } else tm1 = tm0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(conv3d_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(p.tiles_w * tiles_h), (unsigned)(N * p.dblocks), (unsigned)(cout / p.n_tile));
+  conv3d_tc2_kernel<<<grid, kThreads, smem, stream>>>(p, tm0, tm1);
+  B200_CHECK_LAUNCH("conv3d_k3_tc2");
+  return B200_OK;
+}
