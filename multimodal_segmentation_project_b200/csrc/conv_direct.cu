@@ -521,6 +521,9 @@ bool b200_conv3d_wgrad_tc_supported(int c0, int c1, int Cout, int N, int D, int 
 int64_t b200_conv3d_wgrad_tc_workspace(int c0, int c1, int Cout, int N, int D, int H, int W);
 int b200_conv3d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const void* dy, int Cout, float* dw, void* workspace,
                          int N, int D, int H, int W, cudaStream_t stream);
+bool b200_convt2_wgrad_tc_supported(int Cin, int Cout, int N, int D, int H, int W);
+int64_t b200_convt2_wgrad_tc_workspace(int Cin, int Cout, int N, int D, int H, int W);
+int b200_convt2_wgrad_tc(const void* x, const void* gy, float* dw, void* workspace, int N, int D, int H, int W, int Cin, int Cout, cudaStream_t stream);
 static int g_wgrad_impl = 0;  // 0 auto, 1 CUDA-core, 2 tcgen05
 // in_channels == 1 first layer (conv_stem.cu)
 bool b200_conv_stem_supported(int c0, int c1, int cout);
@@ -707,7 +710,12 @@ extern "C" int b200_convt2_bwd_data(int dtype, const void* gy, const float* w, v
 
 extern "C" int64_t b200_convt2_wgrad_workspace(int Cin, int Cout, int N, int D, int H, int W) {
   const SplitPlan sp = plan_split((int64_t)N * D * H * W, Cin, 8 * Cout);
-  return (int64_t)sp.nsplit * Cin * 8 * Cout * 4 + b200_bn_partials_bytes(((Cout + 7) / 8) * 8);
+  int64_t main_bytes = (int64_t)sp.nsplit * Cin * 8 * Cout * 4;
+  if (b200_convt2_wgrad_tc_supported(Cin, Cout, N, D, H, W)) {
+    const int64_t t = b200_convt2_wgrad_tc_workspace(Cin, Cout, N, D, H, W);
+    if (t > main_bytes) main_bytes = t;
+  }
+  return b200_bn_partials_bytes(((Cout + 7) / 8) * 8) + main_bytes;
 }
 
 extern "C" int b200_convt2_bwd_weight(int dtype, const void* x, const void* gy, float* dw, float* dbias, void* workspace,
@@ -717,24 +725,29 @@ extern "C" int b200_convt2_bwd_weight(int dtype, const void* x, const void* gy, 
   cudaStream_t st = (cudaStream_t)stream;
   const Geom g{N, D, H, W};
   const int64_t M = g.rows();
-  const SplitPlan sp = plan_split(M, Cin, 8 * Cout);
-  float* partial = (float*)workspace;
+  float* bpart = (float*)workspace;
+  float* partial = (float*)((uint8_t*)workspace + b200_bn_partials_bytes(((Cout + 7) / 8) * 8));
   int rc;
-  if (dtype == B200_F32) {
-    rc = launch_cols_gemm("convt2_bwd_weight", ColsPlain<float>{(const float*)x, Cin, g}, ColsChild<float>{(const float*)gy, Cout, g}, M, Cin, 8 * Cout, sp, partial, st);
-  } else if (dtype == B200_BF16) {
-    rc = launch_cols_gemm("convt2_bwd_weight", ColsPlain<__nv_bfloat16>{(const __nv_bfloat16*)x, Cin, g},
-                          ColsChild<__nv_bfloat16>{(const __nv_bfloat16*)gy, Cout, g}, M, Cin, 8 * Cout, sp, partial, st);
+  if (dtype == B200_BF16 && g_wgrad_impl != 1 && b200_convt2_wgrad_tc_supported(Cin, Cout, N, D, H, W)) {
+    rc = b200_convt2_wgrad_tc(x, gy, dw, partial, N, D, H, W, Cin, Cout, st);
+    if (rc) return rc;
   } else {
-    B200_FAIL(B200_ERR_UNSUPPORTED, "convt2_bwd_weight: unknown dtype %d", dtype);
+    const SplitPlan sp = plan_split(M, Cin, 8 * Cout);
+    if (dtype == B200_F32) {
+      rc = launch_cols_gemm("convt2_bwd_weight", ColsPlain<float>{(const float*)x, Cin, g}, ColsChild<float>{(const float*)gy, Cout, g}, M, Cin, 8 * Cout, sp, partial, st);
+    } else if (dtype == B200_BF16) {
+      rc = launch_cols_gemm("convt2_bwd_weight", ColsPlain<__nv_bfloat16>{(const __nv_bfloat16*)x, Cin, g},
+                            ColsChild<__nv_bfloat16>{(const __nv_bfloat16*)gy, Cout, g}, M, Cin, 8 * Cout, sp, partial, st);
+    } else {
+      B200_FAIL(B200_ERR_UNSUPPORTED, "convt2_bwd_weight: unknown dtype %d", dtype);
+    }
+    if (rc) return rc;
+    const int64_t total = (int64_t)8 * Cin * Cout;
+    reduce_convt_wgrad_kernel<<<b200_grid_for(total, 256, B200_NUM_SMS * 8), 256, 0, st>>>(partial, sp.nsplit, Cin, Cout, dw);
+    B200_CHECK_LAUNCH("convt2_wgrad_reduce");
   }
-  if (rc) return rc;
-  const int64_t total = (int64_t)8 * Cin * Cout;
-  reduce_convt_wgrad_kernel<<<b200_grid_for(total, 256, B200_NUM_SMS * 8), 256, 0, st>>>(partial, sp.nsplit, Cin, Cout, dw);
-  B200_CHECK_LAUNCH("convt2_wgrad_reduce");
   if (dbias) {
     B200_REQUIRE(Cout % 8 == 0, B200_ERR_UNSUPPORTED, "convt2_bwd_weight: dbias needs Cout %% 8 == 0");
-    float* bpart = partial + (int64_t)sp.nsplit * Cin * 8 * Cout;
     return b200_channel_sum(dtype, gy, M * 8, Cout, bpart, dbias, stream);
   }
   return B200_OK;

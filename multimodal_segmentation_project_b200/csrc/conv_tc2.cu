@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -27,9 +28,9 @@ constexpr int kPlaneVox = kHalo * kHalo;            // 324
 constexpr int kStageBytes = 10496;                  // 324 voxels x 32 B = 10368, rounded up to the 256-byte SWIZZLE_32B period
 constexpr int kStageTx = kPlaneVox * 32;            // bytes written per stage by one TMA box
 constexpr int kMaxStages = 6;
-constexpr int kThreads = 256;                       // w0: act TMA, w1: weight TMA + TMEM alloc, w2: MMA, w4-7: epilogue
+constexpr int kThreads = 384;                       // w0: act TMA, w1: weight TMA + TMEM alloc, w2: MMA, w4-7 / w8-11: epilogue of w-tile 0 / 1
 constexpr int kMaxDseg = 8;
-constexpr int kSmemHeader = 512;
+constexpr int kSmemHeader = 1024;                   // barriers, TMEM slot, bias[<=128]
 
 struct Tc2Params {
   const uint8_t* wpack; const float* bias;
@@ -38,6 +39,7 @@ struct Tc2Params {
   int N, D, H, W;
   int n_tile, dseg, dblocks, slabs, wstages, tmem_cols, tiles_w, stages;
   int kd_per_mma;   // 3 when 3*n_tile <= 256, else 2 (n_tile = 128)
+  int mma_repeat;   // diagnostics only (B200_TC_REPEAT): issue the fused MMAs this many times
 };
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, int c, int w, int h, int d, int n, uint32_t bar) {
@@ -60,7 +62,7 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 conv3d_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -73,6 +75,7 @@ conv3d_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tm0, co
   auto w_empty = [&](int i) { return bar0 + 8u * (14 + i); };
   auto acc_full = [&](int i) { return bar0 + 8u * (16 + i); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+  float* bias_s = reinterpret_cast<float*>(smem + 512);
   uint8_t* act = smem + kSmemHeader;
   uint8_t* wts = act + p.stages * kStageBytes;
 
@@ -100,6 +103,7 @@ conv3d_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tm0, co
     prefetch_tmap(&tm0);
     if (p.c1) prefetch_tmap(&tm1);
   }
+  if (warp >= 4 && threadIdx.x - 128 < p.n_tile) bias_s[threadIdx.x - 128] = p.bias ? p.bias[blockIdx.z * p.n_tile + (threadIdx.x - 128)] : 0.f;
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -133,49 +137,62 @@ conv3d_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tm0, co
   } else if (warp == 2) {
     // ===================== MMA issue =====================
     if (lane == 0) {
+      // The issuing thread is a single in-order lane: keep the per-MMA work to two 32-bit adds.  Descriptors are
+      // split into a constant high word and a low word whose address field (addr >> 4) is advanced by constants.
       const uint32_t n_t = p.n_tile;
       const uint32_t b_lbo = 48u * n_t;        // K-chunk stride of one (kh,kw) B matrix: 3*n rows x 16 B
-      const uint32_t b_tap = 96u * n_t;        // bytes per (kh,kw): 2 chunks x 3*n rows x 16 B
+      const uint32_t b_tap16 = 6u * n_t;       // (bytes per (kh,kw) = 96*n) >> 4
+      const uint64_t a_proto = desc_kmajor_sw32(0, kHalo * 32);
+      const uint64_t b_proto = tc::smem_desc_kmajor_noswz(0, b_lbo, 128);
+      const uint32_t a_hi = (uint32_t)(a_proto >> 32), a_lo0 = (uint32_t)a_proto;
+      const uint32_t b_hi = (uint32_t)(b_proto >> 32), b_lo0 = (uint32_t)b_proto;
+      uint32_t idesc_n[4];
+#pragma unroll
+      for (int i = 1; i <= 3; ++i) idesc_n[i] = tc::idesc_bf16_f32(128, (int)(i * n_t));
+      const bool wt1 = w0 + 8 < p.W;
+      const uint32_t wt_cols = (uint32_t)p.dseg * n_t;
       for (int s = 0; s < p.slabs; ++s) {
         const int ws = s % p.wstages;
         tc::mbar_wait(w_full(ws), (s / p.wstages) & 1);
         tc::tc_fence_after();
-        const uint32_t w_base = tc::smem_u32(wts + (size_t)ws * wbytes);
+        const uint32_t w_lo = b_lo0 + (tc::smem_u32(wts + (size_t)ws * wbytes) >> 4);
         for (int qi = 0; qi < nq; ++qi) {
           const int it = s * nq + qi;
           const int st = it % p.stages;
           tc::mbar_wait(a_full(st), (it / p.stages) & 1);
           tc::tc_fence_after();
           const int q = qi - 1;
-          const uint32_t a_base = tc::smem_u32(act + st * kStageBytes);
+          const uint32_t a_lo = a_lo0 + (tc::smem_u32(act + st * kStageBytes) >> 4);
           // valid kd for this input plane: output plane pl = q + 1 - kd in [0, planes)
           const int kd_lo = max(0, q + 2 - planes), kd_hi = min(2, q + 1);
+          // kd groups of at most kd_per_mma taps; planes q+1-a .. q+1-b occupy ascending TMEM column blocks
+          int ga[2], gn[2], ngroups = 0;
+          for (int a = kd_lo; a <= kd_hi; a += p.kd_per_mma) { ga[ngroups] = a; gn[ngroups] = min(kd_hi, a + p.kd_per_mma - 1) - a + 1; ++ngroups; }
+          const bool first = (s == 0 && kd_lo == 0);  // plane q+1 receives its very first contribution in this stage
+          if (first) {
+            // tap (0,0): kd = 0 overwrites (accumulate = 0) and therefore cannot be fused with planes holding partial sums
+            const uint32_t col = (uint32_t)(p.dseg - 2 - q) * n_t;
+            tc::umma_bf16_ss(tmem_base + col, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | w_lo, idesc_n[1], 0);
+            if (wt1) tc::umma_bf16_ss(tmem_base + wt_cols + col, ((uint64_t)a_hi << 32) | (a_lo + 16), ((uint64_t)b_hi << 32) | w_lo, idesc_n[1], 0);
+            if (kd_hi >= 1) {
+              const uint32_t nrem = (uint32_t)kd_hi;  // kd = 1..kd_hi (<= 2 taps: fits one MMA for every n_tile)
+              const uint64_t bd = ((uint64_t)b_hi << 32) | (w_lo + n_t);  // skip kd = 0 rows: n rows x 16 B >> 4
+              tc::umma_bf16_ss(tmem_base + col + n_t, ((uint64_t)a_hi << 32) | a_lo, bd, idesc_n[nrem], 1);
+              if (wt1) tc::umma_bf16_ss(tmem_base + wt_cols + col + n_t, ((uint64_t)a_hi << 32) | (a_lo + 16), bd, idesc_n[nrem], 1);
+            }
+          }
+          for (int rep = 0; rep < p.mma_repeat; ++rep)
+          for (int gi = 0; gi < ngroups; ++gi) {
+            const uint32_t col = tmem_base + (uint32_t)(p.dseg - 2 - q + ga[gi]) * n_t;
+            const uint32_t idesc = idesc_n[gn[gi]];
+            const uint32_t b_lo_g = w_lo + (uint32_t)ga[gi] * n_t;
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-              const uint32_t a_off = (uint32_t)(kh * kHalo + kw) * 32;
-              const uint32_t b_base = w_base + (uint32_t)(kh * 3 + kw) * b_tap;
-              // kd groups: at the very first contribution of a plane (s == 0, kd == 0, tap (0,0)) the accumulator is
-              // overwritten, so that MMA cannot be fused with planes that already hold partial sums
-              int a = kd_lo;
-              while (a <= kd_hi) {
-                int b = min(kd_hi, a + p.kd_per_mma - 1);
-                uint32_t accumulate = 1;
-                if (s == 0 && kh == 0 && kw == 0 && a == 0) { b = 0; accumulate = 0; }
-                const uint32_t nn = (uint32_t)(b - a + 1) * n_t;
-                const uint32_t idesc = tc::idesc_bf16_f32(128, (int)nn);
-                const uint64_t bdesc = tc::smem_desc_kmajor_noswz(b_base + (uint32_t)a * n_t * 16, b_lbo, 128);
-                // planes q+1-a .. q+1-b occupy ascending column blocks (descending plane order)
-                const uint32_t col = (uint32_t)(p.dseg - 2 - q + a) * n_t;
-#pragma unroll
-                for (int wt = 0; wt < 2; ++wt) {
-                  if (w0 + wt * 8 >= p.W) continue;
-                  const uint64_t adesc = desc_kmajor_sw32(a_base + a_off + wt * 256, kHalo * 32);
-                  tc::umma_bf16_ss(tmem_base + (uint32_t)(wt * p.dseg) * n_t + col, adesc, bdesc, idesc, accumulate);
-                }
-                a = b + 1;
-              }
+            for (int tap = 0; tap < 9; ++tap) {
+              if (first && tap == 0) continue;
+              const uint32_t a_off = (uint32_t)(((tap / 3) * kHalo + (tap % 3)) * 32) >> 4;
+              const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo_g + (uint32_t)tap * b_tap16);
+              tc::umma_bf16_ss(col, ((uint64_t)a_hi << 32) | (a_lo + a_off), bd, idesc, 1);
+              if (wt1) tc::umma_bf16_ss(col + wt_cols, ((uint64_t)a_hi << 32) | (a_lo + a_off + 16), bd, idesc, 1);
             }
           }
           tc::umma_commit(a_empty(st));
@@ -185,18 +202,17 @@ conv3d_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tm0, co
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int ew = warp - 4;
+    // ===================== epilogue: warps 4-7 drain w-tile 0, warps 8-11 w-tile 1 =====================
+    const int wt = (warp - 4) >> 2;
+    const int ew = warp & 3;          // TMEM lane quadrant this warp may touch
     const int m = ew * 32 + lane;
     const int h = h0 + (m >> 3);
-    for (int pl = 0; pl < planes; ++pl) {
-      tc::mbar_wait(acc_full(pl), 0);
-      tc::tc_fence_after();
-#pragma unroll
-      for (int wt = 0; wt < 2; ++wt) {
-        if (w0 + wt * 8 >= p.W) continue;
-        const int w = w0 + wt * 8 + (m & 7);
-        const bool valid = h < p.H && w < p.W;
+    const int w = w0 + wt * 8 + (m & 7);
+    if (w0 + wt * 8 < p.W) {
+      const bool valid = h < p.H && w < p.W;
+      for (int pl = 0; pl < planes; ++pl) {
+        tc::mbar_wait(acc_full(pl), 0);
+        tc::tc_fence_after();
         const int64_t row = (((int64_t)n * p.D + d0 + pl) * p.H + h) * p.W + w;
         const uint32_t col0 = (uint32_t)((wt * p.dseg + (p.dseg - 1 - pl)) * p.n_tile);
         for (int cc = 0; cc < p.n_tile / 16; ++cc) {
@@ -207,9 +223,8 @@ conv3d_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tm0, co
           uint32_t packed[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float a = __uint_as_float(r[2 * i]), b = __uint_as_float(r[2 * i + 1]);
-            if (p.bias) { a += __ldg(p.bias + ch + 2 * i); b += __ldg(p.bias + ch + 2 * i + 1); }
-            __nv_bfloat162 hb = __floats2bfloat162_rn(a, b);
+            const float2 bb = *reinterpret_cast<const float2*>(bias_s + cc * 16 + 2 * i);
+            __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(r[2 * i]) + bb.x, __uint_as_float(r[2 * i + 1]) + bb.y);
             packed[i] = *reinterpret_cast<uint32_t*>(&hb);
           }
           if (valid) {
@@ -308,6 +323,7 @@ int b200_conv3d_k3_tc2(const void* x0, int c0, const void* x1, int c1, const voi
   p.n_tile = n_tile_for(cout);
   p.slabs = (c0 + c1) / 16;
   p.kd_per_mma = 3 * p.n_tile <= 256 ? 3 : 2;
+  { const char* e = getenv("B200_TC_REPEAT"); p.mma_repeat = e ? atoi(e) : 1; if (p.mma_repeat < 1) p.mma_repeat = 1; }
   int dseg = 256 / (2 * p.n_tile);
   if (dseg > kMaxDseg) dseg = kMaxDseg;
   if (dseg < 1) dseg = 1;

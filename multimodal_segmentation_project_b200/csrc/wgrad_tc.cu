@@ -18,6 +18,7 @@
 //     dW to a workspace; a second kernel reduces the partials in fixed order (deterministic).
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "tma_maps.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -27,7 +28,7 @@ using bf16 = __nv_bfloat16;
 constexpr int kQPitch = 24;                          // voxels per halo row (18 used), 768 B = 3 swizzle periods
 constexpr int kQBytes = 18 * kQPitch * 32;           // 13824
 constexpr int kPSlabBytes = 256 * 32;                // one 16-channel slab of a 16x16 plane
-constexpr int kQStages = 3, kPStages = 4;
+constexpr int kQStages = 3, kPStages = 4;   // P planes stay resident for three Q planes (kd = 0,1,2)
 constexpr int kThreads = 288;                        // 4 producer + 4 epilogue + 1 MMA warps
 constexpr int kHeader = 256;
 constexpr int kAccCols = 9 * 48;                     // 432 -> 512 allocated
@@ -42,6 +43,7 @@ struct WgParams {
   int mslabs;                   // 16-channel slabs of P handled per CTA (1..4)
   int dseg, dblocks, tiles_w, tiles_h;
   int m128;                     // issue M=128 MMAs (rows beyond the real channels are ignored)
+  int repeat;                   // diagnostics only (B200_WG_REPEAT)
 };
 
 __device__ __forceinline__ uint32_t swz32(uint32_t off) { return off ^ (((off >> 7) & 1u) << 4); }
@@ -58,7 +60,8 @@ __device__ __forceinline__ uint64_t desc_mn_sw32(uint32_t addr, uint32_t lbo_byt
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad_tc_kernel(const WgParams g) {
+wgrad_tc_kernel(const WgParams g, const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_q0,
+                const __grid_constant__ CUtensorMap tm_q1) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // SWIZZLE_32B patterns repeat every 256 bytes of ABSOLUTE shared-memory address: align the carve-up ourselves
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -84,8 +87,8 @@ wgrad_tc_kernel(const WgParams g) {
   const int planes = min(g.dseg, g.D - d0);
 
   if (warp == 8 && lane == 0) {
-    for (int i = 0; i < kQStages; ++i) { tc::mbar_init(q_full(i), 4); tc::mbar_init(q_empty(i), 1); }
-    for (int i = 0; i < kPStages; ++i) { tc::mbar_init(p_full(i), 4); tc::mbar_init(p_empty(i), 1); }
+    for (int i = 0; i < kQStages; ++i) { tc::mbar_init(q_full(i), 1); tc::mbar_init(q_empty(i), 1); }
+    for (int i = 0; i < kPStages; ++i) { tc::mbar_init(p_full(i), 1); tc::mbar_init(p_empty(i), 1); }
     tc::mbar_init(acc_done, 1);
     tc::fence_barrier_init();
   }
@@ -98,89 +101,36 @@ wgrad_tc_kernel(const WgParams g) {
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // ===================== producers =====================
-    const int tid = threadIdx.x;
-    const int cpo = mchunk * 64;                       // first P channel of this CTA
-    const int pieces = g.mslabs * 2;                   // 16-byte pieces per P voxel
-    const int qc = qslab * 16;
-    const bf16* qbase; int qcs, qoff;
-    if (qc < g.cq0) { qbase = g.q0; qcs = g.cq0; qoff = qc; } else { qbase = g.q1; qcs = g.cq1; qoff = qc - g.cq0; }
-    int pcount = 0, qcount = 0;
-    for (int i = 0; i <= planes + 1; ++i) {
-      if (i < planes) {
-        // ---- P plane i : 16x16 voxels x (mslabs*16) channels
-        const int st = pcount % kPStages;
-        tc::mbar_wait(p_empty(st), ((pcount / kPStages) & 1) ^ 1);
-        uint8_t* dst = pbuf + st * p_stage_bytes;
-        const int d = d0 + i;
-        const int items = 256 * pieces;
-        for (int base = 0; base < items; base += 128 * 8) {
-          uint4 v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int id = base + tid + 128 * j;
-            v[j] = make_uint4(0, 0, 0, 0);
-            if (id < items) {
-              const int vox = id / pieces, pc = id - vox * pieces;
-              const int h = h0 + (vox >> 4), w = w0 + (vox & 15);
-              if (h < g.H && w < g.W && cpo + pc * 8 < g.cp) {
-                const int64_t row = (((int64_t)n * g.D + d) * g.H + h) * g.W + w;
-                v[j] = __ldg(reinterpret_cast<const uint4*>(g.p + row * g.cp + cpo + pc * 8));
-              }
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int id = base + tid + 128 * j;
-            if (id < items) {
-              const int vox = id / pieces, pc = id - vox * pieces;
-              const uint32_t off = (uint32_t)(pc >> 1) * kPSlabBytes + swz32((uint32_t)vox * 32 + (pc & 1) * 16);
-              *reinterpret_cast<uint4*>(dst + off) = v[j];
-            }
-          }
+  if (warp == 0) {
+    // ===================== producer: one thread drives the TMA unit =====================
+    // P plane i  : mslabs boxes of 16 ch x 16 (w) x 16 (h)  -> [slab][voxel][16 ch]
+    // Q plane i-1: one box of 16 ch x 24 (w) x 18 (h) at (w0-1, h0-1) -> halo rows of 24 voxels (18 used)
+    // out-of-volume voxels / channels are zero-filled by the TMA unit (conv padding, ragged tiles)
+    if (lane == 0) {
+      tma::prefetch(&tm_p);
+      tma::prefetch(&tm_q0);
+      const int cpo = mchunk * 64;
+      const int qc = qslab * 16;
+      const CUtensorMap* tq = qc < g.cq0 ? &tm_q0 : &tm_q1;
+      const int qoff = qc < g.cq0 ? qc : qc - g.cq0;
+      int pcount = 0, qcount = 0;
+      for (int i = 0; i <= planes + 1; ++i) {
+        if (i < planes) {
+          const int st = pcount % kPStages;
+          tc::mbar_wait(p_empty(st), ((pcount / kPStages) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(p_full(st), p_stage_bytes);
+          const uint32_t dst = tc::smem_u32(pbuf + st * p_stage_bytes);
+          for (int ms = 0; ms < g.mslabs; ++ms)
+            tma::load_5d(dst + ms * kPSlabBytes, &tm_p, cpo + ms * 16, w0, h0, d0 + i, n, p_full(st));
+          ++pcount;
         }
-        tc::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(p_full(st));
-        ++pcount;
-      }
-      {
-        // ---- Q plane q = i - 1 : 18x18 halo voxels x 16 channels
-        const int q = i - 1;
-        const int st = qcount % kQStages;
-        tc::mbar_wait(q_empty(st), ((qcount / kQStages) & 1) ^ 1);
-        uint8_t* dst = qbuf + st * kQBytes;
-        const int d = d0 + q;
-        const bool dvalid = (unsigned)d < (unsigned)g.D;
-        uint4 v[6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          const int id = tid + 128 * j;
-          v[j] = make_uint4(0, 0, 0, 0);
-          if (id < 648) {
-            const int vox = id >> 1, pc = id & 1;
-            const int hh = vox / 18, ww = vox - hh * 18;
-            const int h = h0 + hh - 1, w = w0 + ww - 1;
-            if (dvalid && (unsigned)h < (unsigned)g.H && (unsigned)w < (unsigned)g.W) {
-              const int64_t row = (((int64_t)n * g.D + d) * g.H + h) * g.W + w;
-              v[j] = __ldg(reinterpret_cast<const uint4*>(qbase + row * qcs + qoff + pc * 8));
-            }
-          }
+        {
+          const int st = qcount % kQStages;
+          tc::mbar_wait(q_empty(st), ((qcount / kQStages) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(q_full(st), kQBytes);
+          tma::load_5d(tc::smem_u32(qbuf + st * kQBytes), tq, qoff, w0 - 1, h0 - 1, d0 + i - 1, n, q_full(st));
+          ++qcount;
         }
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          const int id = tid + 128 * j;
-          if (id < 648) {
-            const int vox = id >> 1, pc = id & 1;
-            const int hh = vox / 18, ww = vox - hh * 18;
-            *reinterpret_cast<uint4*>(dst + swz32((uint32_t)(hh * kQPitch + ww) * 32 + pc * 16)) = v[j];
-          }
-        }
-        tc::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(q_full(st));
-        ++qcount;
       }
     }
   } else if (warp == 8) {
@@ -189,6 +139,10 @@ wgrad_tc_kernel(const WgParams g) {
       // M = 64, N = 48, A and B MN-major
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((48u >> 3) << 17) | ((g.m128 ? (128u >> 4) : (64u >> 4)) << 24);
       const uint32_t a_lbo = g.mslabs > 1 ? kPSlabBytes : 0;   // M-group (16 ch) stride; rows beyond the real channels are ignored
+      // all stage bases are 256-byte aligned, so the descriptor base-offset field stays 0
+      const uint64_t a_proto = desc_mn_sw32(0, a_lbo, 256), b_proto = desc_mn_sw32(0, 32, 256);
+      const uint32_t a_hi = (uint32_t)(a_proto >> 32), a_lo0 = (uint32_t)a_proto;
+      const uint32_t b_hi = (uint32_t)(b_proto >> 32), b_lo0 = (uint32_t)b_proto;
       uint32_t touched = 0;
       int p_ready = 0;  // number of P planes whose full-barrier has been observed
       for (int qi = 0; qi <= planes + 1; ++qi) {
@@ -202,20 +156,23 @@ wgrad_tc_kernel(const WgParams g) {
         }
         tc::tc_fence_after();
         const uint32_t q_base = tc::smem_u32(qbuf + qst * kQBytes);
+        // single in-order issuing lane: descriptors = constant high word + low word advanced by constants
+        const uint32_t q_lo = b_lo0 + (q_base >> 4);
 #pragma unroll
         for (int kd = 0; kd < 3; ++kd) {
           const int pl = q - kd + 1;
           if (pl < 0 || pl >= planes) continue;
-          const uint32_t p_base = tc::smem_u32(pbuf + (pl % kPStages) * p_stage_bytes);
+          const uint32_t p_lo = a_lo0 + (tc::smem_u32(pbuf + (pl % kPStages) * p_stage_bytes) >> 4);
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
             const uint32_t d_tmem = tmem_base + (uint32_t)((kd * 3 + kh) * 48);
-            uint32_t acc = (touched >> (kd * 3 + kh)) & 1u;
+            const uint32_t acc0 = (touched >> (kd * 3 + kh)) & 1u;
+            for (int rep = 0; rep < g.repeat; ++rep)
+#pragma unroll
             for (int r = 0; r < 16; ++r) {
-              const uint64_t adesc = desc_mn_sw32(p_base + r * 512, a_lbo, 256);
-              const uint64_t bdesc = desc_mn_sw32(q_base + (r + kh) * (kQPitch * 32), 32, 256);
-              tc::umma_bf16_ss(d_tmem, adesc, bdesc, idesc, acc);
-              acc = 1;
+              const uint64_t adesc = ((uint64_t)a_hi << 32) | (p_lo + (uint32_t)(r * 512 >> 4));
+              const uint64_t bdesc = ((uint64_t)b_hi << 32) | (q_lo + (uint32_t)((r + kh) * (kQPitch * 32) >> 4));
+              tc::umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (r == 0 && rep == 0) ? acc0 : 1u);
             }
             touched |= 1u << (kd * 3 + kh);
           }
@@ -225,7 +182,7 @@ wgrad_tc_kernel(const WgParams g) {
       }
       tc::umma_commit(acc_done);
     }
-  } else {
+  } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> partial dW =====================
     const int ew = warp - 4;
     tc::mbar_wait(acc_done, 0);
@@ -304,7 +261,240 @@ WgPlan make_plan(int c0, int c1, int Cout, int N, int D, int H, int W) {
   return pl;
 }
 
+
+// =====================================================================================================
+// ConvTranspose3d(k=2,s=2) weight gradient on the tensor cores (models/unet.py:56-58):
+//     dW[ci][co][child] = sum_v x[v][ci] * gy[child(v)][co],   child = (dz,dy,dx) of the 2x finer grid
+// Same MN-major / SWIZZLE_32B machinery as above: M = 64 input channels of x (TMA boxes), K = 16 coarse
+// voxels of one tile row, N = 8 children x 16 output channels = 128: producer warps gather the eight
+// child planes of gy into [child][voxel][16 ch] so that the children are the B descriptor's
+// leading-dimension stride.  One 64 x 128 fp32 accumulator in TMEM per CTA, partials reduced in fixed order.
+// =====================================================================================================
+constexpr int kCtThreads = 320;          // 4 gather warps, 4 epilogue warps, MMA warp, TMA warp
+constexpr int kCtStages = 2;
+constexpr int kCtQBytes = 8 * kPSlabBytes;  // 8 child planes of 16x16 voxels x 16 ch
+
+struct CtParams {
+  const bf16* gy; int cout;   // fine grid [N,2D,2H,2W,cout]
+  int cin;
+  float* partial;             // [cta][mrows][128]
+  int mrows, mslabs;
+  int N, D, H, W;             // coarse geometry
+  int dseg, dblocks, tiles_w, tiles_h;
+};
+
+__global__ void __launch_bounds__(kCtThreads, 1)
+convt_wgrad_tc_kernel(const CtParams g, const __grid_constant__ CUtensorMap tm_x) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t bar0 = tc::smem_u32(bars);
+  auto q_full = [&](int i) { return bar0 + 8u * i; };
+  auto q_empty = [&](int i) { return bar0 + 8u * (2 + i); };
+  auto p_full = [&](int i) { return bar0 + 8u * (4 + i); };
+  auto p_empty = [&](int i) { return bar0 + 8u * (6 + i); };
+  const uint32_t acc_done = bar0 + 8u * 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 192);
+  const uint32_t p_stage_bytes = (uint32_t)g.mslabs * kPSlabBytes;
+  uint8_t* pbuf = smem + kHeader;
+  uint8_t* qbuf = pbuf + kCtStages * p_stage_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tw = blockIdx.x % g.tiles_w, th = blockIdx.x / g.tiles_w % g.tiles_h;
+  const int rest = blockIdx.x / (g.tiles_w * g.tiles_h);
+  const int n = rest / g.dblocks, db = rest % g.dblocks;
+  const int mchunk = blockIdx.y, qslab = blockIdx.z;
+  const int w0 = tw * 16, h0 = th * 16, d0 = db * g.dseg;
+  const int planes = min(g.dseg, g.D - d0);
+
+  if (warp == 8 && lane == 0) {
+    for (int i = 0; i < kCtStages; ++i) {
+      tc::mbar_init(q_full(i), 4); tc::mbar_init(q_empty(i), 1);
+      tc::mbar_init(p_full(i), 1); tc::mbar_init(p_empty(i), 1);
+    }
+    tc::mbar_init(acc_done, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 4) {
+    tc::tmem_alloc(tc::smem_u32(tmem_slot), 128);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ---- gather the 8 child planes of gy for coarse plane d0+i: [child][voxel][16 ch], SWIZZLE_32B
+    const int tid = threadIdx.x;
+    const int FH = 2 * g.H, FW = 2 * g.W, FD = 2 * g.D;
+    const int qoff = qslab * 16;
+    for (int i = 0; i < planes; ++i) {
+      const int st = i % kCtStages;
+      tc::mbar_wait(q_empty(st), ((i / kCtStages) & 1) ^ 1);
+      uint8_t* dst = qbuf + st * kCtQBytes;
+      const int d = d0 + i;
+      for (int base = 0; base < 8 * 256 * 2; base += 128 * 8) {
+        uint4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // item -> (child, coarse voxel, 16-byte piece); consecutive lanes walk the fine row: (w, dx, piece)
+          const int id = base + tid + 128 * j;
+          const int pc = id & 1, dx = (id >> 1) & 1, wv = (id >> 2) & 15, dy = (id >> 6) & 1, hv = (id >> 7) & 15, dz = id >> 11;
+          const int fh = 2 * (h0 + hv) + dy, fw = 2 * (w0 + wv) + dx, fd = 2 * d + dz;
+          v[j] = make_uint4(0, 0, 0, 0);
+          if (h0 + hv < g.H && w0 + wv < g.W && fd < FD) {
+            const int64_t row = (((int64_t)n * FD + fd) * FH + fh) * FW + fw;
+            v[j] = __ldg(reinterpret_cast<const uint4*>(g.gy + row * g.cout + qoff + pc * 8));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int id = base + tid + 128 * j;
+          const int pc = id & 1, dx = (id >> 1) & 1, wv = (id >> 2) & 15, dy = (id >> 6) & 1, hv = (id >> 7) & 15, dz = id >> 11;
+          const int child = dz * 4 + dy * 2 + dx;
+          *reinterpret_cast<uint4*>(dst + child * kPSlabBytes + swz32((uint32_t)(hv * 16 + wv) * 32 + pc * 16)) = v[j];
+        }
+      }
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(q_full(st));
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      tma::prefetch(&tm_x);
+      for (int i = 0; i < planes; ++i) {
+        const int st = i % kCtStages;
+        tc::mbar_wait(p_empty(st), ((i / kCtStages) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(p_full(st), p_stage_bytes);
+        for (int ms = 0; ms < g.mslabs; ++ms)
+          tma::load_5d(tc::smem_u32(pbuf + st * p_stage_bytes + ms * kPSlabBytes), &tm_x, mchunk * 64 + ms * 16, w0, h0, d0 + i, n, p_full(st));
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      // M = 64 (x channels), N = 128 (child, 16 co), both MN-major
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((64u >> 4) << 24);
+      const uint64_t a_proto = desc_mn_sw32(0, g.mslabs > 1 ? kPSlabBytes : 0, 256), b_proto = desc_mn_sw32(0, kPSlabBytes, 256);
+      const uint32_t a_hi = (uint32_t)(a_proto >> 32), a_lo0 = (uint32_t)a_proto;
+      const uint32_t b_hi = (uint32_t)(b_proto >> 32), b_lo0 = (uint32_t)b_proto;
+      for (int i = 0; i < planes; ++i) {
+        const int st = i % kCtStages;
+        const uint32_t ph = (i / kCtStages) & 1;
+        tc::mbar_wait(p_full(st), ph);
+        tc::mbar_wait(q_full(st), ph);
+        tc::tc_fence_after();
+        const uint32_t p_lo = a_lo0 + (tc::smem_u32(pbuf + st * p_stage_bytes) >> 4);
+        const uint32_t q_lo = b_lo0 + (tc::smem_u32(qbuf + st * kCtQBytes) >> 4);
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+          tc::umma_bf16_ss(tmem_base, ((uint64_t)a_hi << 32) | (p_lo + r * 32), ((uint64_t)b_hi << 32) | (q_lo + r * 32), idesc, (i | r) != 0);
+        tc::umma_commit(p_empty(st));
+        tc::umma_commit(q_empty(st));
+      }
+      tc::umma_commit(acc_done);
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    tc::mbar_wait(acc_done, 0);
+    tc::tc_fence_after();
+    const int m_real = min(64, g.cin - mchunk * 64);
+    const int ci = ew * 16 + lane;  // M = 64: row m in TMEM lane (m % 16) + 32 * (m / 16)
+    const int64_t cta = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    float* out = g.partial + cta * (int64_t)(g.mrows * 128);
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      uint32_t r[16];
+      tc::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(cc * 16), r);
+      tc::tmem_ld_wait();
+      if (lane < 16 && ci < m_real) {
+        float4* dst = reinterpret_cast<float4*>(out + (int64_t)ci * 128 + cc * 16);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          dst[k] = make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]));
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tmem_base, 128);
+}
+
+// partial[(qslab, mchunk, spatial)][m][child*16 + col] -> dw[ci][co][child]
+__global__ void convt_wgrad_tc_reduce_kernel(const float* __restrict__ partial, int spatial, int mchunks, int mrows, int Cin, int Cout,
+                                             float* __restrict__ dw) {
+  const int64_t total = (int64_t)Cin * Cout * 8;
+  const int64_t stride = (int64_t)mrows * 128;
+  const int lane = threadIdx.x & 31;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < total; i += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int child = (int)(i % 8);
+    const int co = (int)((i / 8) % Cout);
+    const int ci = (int)(i / (8 * (int64_t)Cout));
+    const int mchunk = ci / 64, mm = ci % 64, qslab = co / 16, cl = co % 16;
+    const float* src = partial + (((int64_t)qslab * mchunks + mchunk) * spatial) * stride + (int64_t)mm * 128 + child * 16 + cl;
+    double s = 0.0;
+    for (int c = lane; c < spatial; c += 32) s += (double)src[(int64_t)c * stride];
+    s = warp_sum_d(s);
+    if (lane == 0) dw[i] = (float)s;
+  }
+}
+
+struct CtPlan { int mslabs, mchunks, qslabs, mrows, dseg, dblocks, tiles_w, tiles_h, spatial; size_t smem; };
+CtPlan make_ct_plan(int Cin, int Cout, int N, int D, int H, int W) {
+  CtPlan pl;
+  pl.mchunks = (Cin + 63) / 64;
+  pl.mslabs = Cin >= 64 ? 4 : Cin / 16;
+  pl.mrows = Cin < 64 ? Cin : 64;
+  pl.qslabs = Cout / 16;
+  pl.tiles_w = (W + 15) / 16;
+  pl.tiles_h = (H + 15) / 16;
+  const int64_t base = (int64_t)pl.tiles_w * pl.tiles_h * N * pl.mchunks * pl.qslabs;
+  int dseg = 8;
+  while (dseg > 1 && base * ((D + dseg - 1) / dseg) < 2 * B200_NUM_SMS) dseg >>= 1;
+  if (dseg > D) dseg = D;
+  pl.dseg = dseg;
+  pl.dblocks = (D + dseg - 1) / dseg;
+  pl.spatial = pl.tiles_w * pl.tiles_h * N * pl.dblocks;
+  pl.smem = kHeader + (size_t)kCtStages * (pl.mslabs * kPSlabBytes + kCtQBytes) + 1024;
+  return pl;
+}
+
 }  // namespace
+
+bool b200_convt2_wgrad_tc_supported(int Cin, int Cout, int N, int D, int H, int W) {
+  if (Cin % 16 || Cout % 16 || (Cin > 64 && Cin % 64)) return false;
+  return N > 0 && D > 0 && H > 0 && W > 0;
+}
+int64_t b200_convt2_wgrad_tc_workspace(int Cin, int Cout, int N, int D, int H, int W) {
+  const CtPlan pl = make_ct_plan(Cin, Cout, N, D, H, W);
+  return (int64_t)pl.spatial * pl.mchunks * pl.qslabs * pl.mrows * 128 * 4;
+}
+int b200_convt2_wgrad_tc(const void* x, const void* gy, float* dw, void* workspace, int N, int D, int H, int W, int Cin, int Cout,
+                         cudaStream_t stream) {
+  B200_REQUIRE(b200_convt2_wgrad_tc_supported(Cin, Cout, N, D, H, W), B200_ERR_UNSUPPORTED, "convt2_wgrad(tcgen05): unsupported channel counts");
+  const CtPlan pl = make_ct_plan(Cin, Cout, N, D, H, W);
+  CtParams g;
+  g.gy = (const bf16*)gy; g.cout = Cout; g.cin = Cin;
+  g.partial = (float*)workspace; g.mrows = pl.mrows; g.mslabs = pl.mslabs;
+  g.N = N; g.D = D; g.H = H; g.W = W;
+  g.dseg = pl.dseg; g.dblocks = pl.dblocks; g.tiles_w = pl.tiles_w; g.tiles_h = pl.tiles_h;
+  CUtensorMap tm_x;
+  int rc = tma::make_ndhwc_map(&tm_x, x, Cin, N, D, H, W, 16, 16);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(convt_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)pl.spatial, (unsigned)pl.mchunks, (unsigned)pl.qslabs);
+  convt_wgrad_tc_kernel<<<grid, kCtThreads, pl.smem, stream>>>(g, tm_x);
+  B200_CHECK_LAUNCH("convt2_wgrad_tc");
+  const int64_t total = (int64_t)Cin * Cout * 8;
+  convt_wgrad_tc_reduce_kernel<<<b200_grid_for(total * 32, 256, B200_NUM_SMS * 16), 256, 0, stream>>>((const float*)workspace, pl.spatial, pl.mchunks,
+                                                                                                    pl.mrows, Cin, Cout, dw);
+  B200_CHECK_LAUNCH("convt2_wgrad_tc_reduce");
+  return B200_OK;
+}
 
 bool b200_conv3d_wgrad_tc_supported(int c0, int c1, int Cout, int N, int D, int H, int W) {
   if (c0 <= 0 || c0 % 16 || c1 % 16 || Cout % 16) return false;
@@ -336,6 +526,9 @@ int b200_conv3d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const v
   {
     const char* e = getenv("B200_WGRAD_M128");
     g.m128 = e ? atoi(e) : 0;
+    const char* e2 = getenv("B200_WG_REPEAT");
+    g.repeat = e2 ? atoi(e2) : 1;
+    if (g.repeat < 1) g.repeat = 1;
   }
   g.mslabs = pl.mslabs; g.dseg = pl.dseg; g.dblocks = pl.dblocks; g.tiles_w = pl.tiles_w; g.tiles_h = pl.tiles_h;
   static bool attr_set = false;
@@ -344,8 +537,14 @@ int b200_conv3d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const v
     attr_set = true;
   }
   B200_REQUIRE(pl.mchunks <= 65535 && pl.qslabs <= 65535, B200_ERR_UNSUPPORTED, "conv3d_wgrad(tcgen05): grid too large");
+  CUtensorMap tm_p, tm_q0, tm_q1;
+  int rc = tma::make_ndhwc_map(&tm_p, g.p, g.cp, N, D, H, W, 16, 16);
+  if (rc) return rc;
+  rc = tma::make_ndhwc_map(&tm_q0, g.q0, g.cq0, N, D, H, W, kQPitch, 18);
+  if (rc) return rc;
+  if (g.cq1) { rc = tma::make_ndhwc_map(&tm_q1, g.q1, g.cq1, N, D, H, W, kQPitch, 18); if (rc) return rc; } else tm_q1 = tm_q0;
   dim3 grid((unsigned)pl.spatial, (unsigned)pl.mchunks, (unsigned)pl.qslabs);
-  wgrad_tc_kernel<<<grid, kThreads, pl.smem, stream>>>(g);
+  wgrad_tc_kernel<<<grid, kThreads, pl.smem, stream>>>(g, tm_p, tm_q0, tm_q1);
   B200_CHECK_LAUNCH("conv3d_wgrad_tc");
   const int64_t total = (int64_t)Cout * (c0 + c1) * 27;
   wgrad_tc_reduce_kernel<<<b200_grid_for(total * 32, 256, B200_NUM_SMS * 16), 256, 0, stream>>>((const float*)workspace, pl.spatial, pl.mchunks, g.mrows,
