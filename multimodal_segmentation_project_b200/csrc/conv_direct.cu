@@ -521,6 +521,16 @@ bool b200_conv3d_wgrad_tc_supported(int c0, int c1, int Cout, int N, int D, int 
 int64_t b200_conv3d_wgrad_tc_workspace(int c0, int c1, int Cout, int N, int D, int H, int W);
 int b200_conv3d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const void* dy, int Cout, float* dw, void* workspace,
                          int N, int D, int H, int W, cudaStream_t stream);
+// second-generation tcgen05 weight gradient (wgrad_tc2.cu): kw taps on the M side, kh taps on the N side
+bool b200_conv3d_wgrad_tc2_supported(int c0, int c1, int Cout, int N, int D, int H, int W);
+int64_t b200_conv3d_wgrad_tc2_workspace(int c0, int c1, int Cout, int N, int D, int H, int W);
+int b200_conv3d_wgrad_tc2(const void* x0, int c0, const void* x1, int c1, const void* dy, int Cout, float* dw, void* workspace,
+                          int N, int D, int H, int W, cudaStream_t stream);
+static int wg_version() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200_WGRAD_TC_VERSION"); v = e ? atoi(e) : 2; }
+  return v;
+}
 bool b200_convt2_wgrad_tc_supported(int Cin, int Cout, int N, int D, int H, int W);
 int64_t b200_convt2_wgrad_tc_workspace(int Cin, int Cout, int N, int D, int H, int W);
 int b200_convt2_wgrad_tc(const void* x, const void* gy, float* dw, void* workspace, int N, int D, int H, int W, int Cin, int Cout, cudaStream_t stream);
@@ -616,6 +626,10 @@ extern "C" int64_t b200_conv3d_wgrad_workspace(int c0, int c1, int Cout, int N, 
     const int64_t t = b200_conv3d_wgrad_tc_workspace(c0, c1, Cout, N, D, H, W);
     if (t > main_bytes) main_bytes = t;
   }
+  if (b200_conv3d_wgrad_tc2_supported(c0, c1, Cout, N, D, H, W)) {
+    const int64_t t = b200_conv3d_wgrad_tc2_workspace(c0, c1, Cout, N, D, H, W);
+    if (t > main_bytes) main_bytes = t;
+  }
   if (b200_conv_stem_wgrad_supported(c0, c1, Cout) && b200_conv_stem_wgrad_workspace(Cout) > main_bytes)
     main_bytes = b200_conv_stem_wgrad_workspace(Cout);
   return b200_bn_partials_bytes(((Cout + 7) / 8) * 8) + main_bytes;
@@ -633,14 +647,18 @@ extern "C" int b200_conv3d_wgrad(int dtype, const void* x0, int c0, const void* 
   const int Cin = c0 + c1, R = 27 * Cin;
   float* bpart = (float*)workspace;
   float* partial = (float*)((uint8_t*)workspace + b200_bn_partials_bytes(((Cout + 7) / 8) * 8));
-  const bool tc_ok = dtype == B200_BF16 && b200_conv3d_wgrad_tc_supported(c0, c1, Cout, N, D, H, W);
+  // v2 (kw on M, kh on N) wins while the channel counts are small; for wide layers v1 fills its 64 M rows with real channels
+  const bool use_v2 = wg_version() == 2 && (int64_t)(c0 + c1) * Cout <= 4096 && b200_conv3d_wgrad_tc2_supported(c0, c1, Cout, N, D, H, W);
+  const bool tc_ok = dtype == B200_BF16 && (use_v2 ? b200_conv3d_wgrad_tc2_supported(c0, c1, Cout, N, D, H, W)
+                                                   : b200_conv3d_wgrad_tc_supported(c0, c1, Cout, N, D, H, W));
   B200_REQUIRE(g_wgrad_impl != 2 || tc_ok, B200_ERR_UNSUPPORTED, "conv3d_wgrad: tcgen05 path forced but unsupported for this problem");
   int rc;
   if (b200_conv_stem_wgrad_supported(c0, c1, Cout) && (dtype == B200_F32 || dtype == B200_BF16)) {
     rc = b200_conv_stem_wgrad(dtype, x0, dy, Cout, dw, partial, N, D, H, W, st);
     if (rc) return rc;
   } else if (tc_ok && g_wgrad_impl != 1) {
-    rc = b200_conv3d_wgrad_tc(x0, c0, x1, c1, dy, Cout, dw, partial, N, D, H, W, st);
+    rc = use_v2 ? b200_conv3d_wgrad_tc2(x0, c0, x1, c1, dy, Cout, dw, partial, N, D, H, W, st)
+                : b200_conv3d_wgrad_tc(x0, c0, x1, c1, dy, Cout, dw, partial, N, D, H, W, st);
     if (rc) return rc;
   } else {
     const SplitPlan sp = plan_split(M, R, Cout);
