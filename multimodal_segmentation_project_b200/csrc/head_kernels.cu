@@ -133,6 +133,83 @@ conv1x1_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const f
   }
 }
 
+// Fast path for the network's actual head (Cin = 16, Cout <= 4): one thread per voxel keeps the whole
+// dW/db tile (Cout*(Cin+1) accumulators) in registers over a grid-stride loop; HBM-bound:
+// 4*Cout B (gy) + 2*Cin B (x) read, 2*Cin B (gx) written per voxel.
+template <typename T, int CIN, int COUT>
+__global__ void __launch_bounds__(kThreads)
+conv1x1_bwd_small_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ gy, T* __restrict__ gx,
+                         float* __restrict__ partials, int64_t N, int64_t S) {
+  __shared__ float ws[COUT * CIN];
+  __shared__ float red[kThreads / 32][COUT * (CIN + 1)];
+  for (int i = threadIdx.x; i < COUT * CIN; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  float dw[COUT][CIN], db[COUT];
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) {
+    db[co] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) dw[co][ci] = 0.f;
+  }
+  const int64_t total = N * S;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = v / S, s = v - n * S;
+    float g[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) g[co] = __ldcs(gy + (n * COUT + co) * S + s);
+    float xf[CIN];
+#pragma unroll
+    for (int c8 = 0; c8 < CIN / 8; ++c8) {
+      Vec8<T> xv;
+      xv.load(x + v * CIN + c8 * 8);
+      float f[8];
+      xv.get(f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) xf[c8 * 8 + k] = f[k];
+    }
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+      db[co] += g[co];
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) dw[co][ci] = fmaf(g[co], xf[ci], dw[co][ci]);
+    }
+    if (gx) {
+#pragma unroll
+      for (int c8 = 0; c8 < CIN / 8; ++c8) {
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float a = 0.f;
+#pragma unroll
+          for (int co = 0; co < COUT; ++co) a = fmaf(g[co], ws[co * CIN + c8 * 8 + k], a);
+          o[k] = a;
+        }
+        Vec8<T> ov;
+        ov.set(o);
+        ov.store(gx + v * CIN + c8 * 8);
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) {
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      const float t = warp_sum(dw[co][ci]);
+      if (lane == 0) red[warp][co * (CIN + 1) + ci] = t;
+    }
+    const float t = warp_sum(db[co]);
+    if (lane == 0) red[warp][co * (CIN + 1) + CIN] = t;
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < COUT * (CIN + 1); p += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < kThreads / 32; ++wq) t += red[wq][p];
+    partials[(int64_t)blockIdx.x * (COUT * (CIN + 1)) + p] = t;
+  }
+}
+
 __global__ void conv1x1_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int Cin, int Cout,
                                             float* __restrict__ dw, float* __restrict__ db) {
   const int Cin1 = Cin + 1, P = Cout * Cin1;
@@ -256,8 +333,15 @@ extern "C" int b200_conv1x1_bwd(int dtype, const void* x, const float* w, const 
   const int groups = kThreads / P > 0 ? kThreads / P : 1;
   const size_t smem = (size_t)(Cout * Cin + kTileV * (Cin + 1) + Cout * kTileV + (size_t)(groups > 1 ? groups : 1) * P) * sizeof(float);
   B200_REQUIRE(smem <= 200 * 1024, B200_ERR_UNSUPPORTED, "conv1x1_bwd: channel counts too large for shared memory");
-  const int nblocks = bwd_blocks(N * S);
-  if (dtype == B200_F32) {
+  int nblocks = bwd_blocks(N * S);
+  if (Cin == 16 && (Cout == 4 || Cout == 2 || Cout == 3)) {
+    nblocks = b200_grid_for(N * S, kThreads, kMaxPartialBlocks);
+#define RUN_SMALL(T, CO) conv1x1_bwd_small_kernel<T, 16, CO><<<nblocks, kThreads, 0, st>>>((const T*)x, w, gy, (T*)gx, partials, N, S)
+    if (dtype == B200_F32) { if (Cout == 4) RUN_SMALL(float, 4); else if (Cout == 3) RUN_SMALL(float, 3); else RUN_SMALL(float, 2); }
+    else if (dtype == B200_BF16) { if (Cout == 4) RUN_SMALL(__nv_bfloat16, 4); else if (Cout == 3) RUN_SMALL(__nv_bfloat16, 3); else RUN_SMALL(__nv_bfloat16, 2); }
+    else B200_FAIL(B200_ERR_UNSUPPORTED, "conv1x1_bwd: unknown dtype %d", dtype);
+#undef RUN_SMALL
+  } else if (dtype == B200_F32) {
     if (smem > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(conv1x1_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conv1x1_bwd_kernel<float><<<nblocks, kThreads, smem, st>>>((const float*)x, w, gy, (float*)gx, partials, N, S, Cin, Cout);
   } else if (dtype == B200_BF16) {

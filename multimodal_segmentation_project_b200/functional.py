@@ -233,7 +233,11 @@ class _ConvBNAct(torch.autograd.Function):
         )
         dw = db = None
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
-            dw, db = conv3d_wgrad_raw(x0, x1, dconv, want_bias=True)
+            # A conv bias feeding a batch-statistics BatchNorm has an exactly-zero gradient (the mean subtraction
+            # cancels it; the reference computes round-off noise around 0): skip the column-sum pass.
+            dw, db = conv3d_wgrad_raw(x0, x1, dconv, want_bias=not ctx.training)
+            if db is None:
+                db = torch.zeros(Cout, dtype=torch.float32, device=dev)
         dx0 = dx1 = None
         if ctx.needs_input_grad[0] or (x1 is not None and ctx.needs_input_grad[1]):
             c0 = x0.shape[-1]
