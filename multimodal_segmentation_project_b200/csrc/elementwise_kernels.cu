@@ -85,6 +85,8 @@ __device__ __forceinline__ void block_channel_reduce(F&& body, int64_t M, int C,
 #pragma unroll
   for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
   if (r < rows_per_iter) {
+    // 4 rows in flight per thread: the loads of the unrolled iterations are independent (read-only inputs)
+#pragma unroll 4
     for (int64_t row = (int64_t)blockIdx.x * rows_per_iter + r; row < M; row += (int64_t)gridDim.x * rows_per_iter)
       body(row, cv, a0, a1);
   }
@@ -182,6 +184,7 @@ bn_act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __res
                   int C) {
   const int CV = C / 8;
   const int64_t total = N * S * CV;
+#pragma unroll 4
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int cv = (int)(i % CV);
     const int64_t row = i / CV;
@@ -270,6 +273,7 @@ bn_act_bwd_apply_kernel(const T* __restrict__ gy, const T* __restrict__ x, T* __
                         int64_t N, int64_t S, int C) {
   const int CV = C / 8;
   const int64_t total = N * S * CV;
+#pragma unroll 4
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int cv = (int)(i % CV);
     const int64_t row = i / CV;

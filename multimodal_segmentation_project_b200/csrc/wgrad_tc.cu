@@ -215,11 +215,13 @@ wgrad_tc_kernel(const WgParams g, const __grid_constant__ CUtensorMap tm_p, cons
 
 // partial[(qslab, mchunk, spatial cta)][m 64][tap 27][n 16] -> dw[co][ci][27]
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int spatial, int mchunks, int mrows, int Cout, int Cin,
-                                       int swapped, float* __restrict__ dw) {
+                                       int swapped, float* __restrict__ dw, int lanes_per_out) {
   const int64_t stride = (int64_t)mrows * 27 * 16;
   const int64_t total = (int64_t)Cout * Cin * 27;
-  const int lane = threadIdx.x & 31;
-  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < total; i += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+  // lanes_per_out = 32: one warp per output (many partials); 1: one thread per output (few partials, many outputs)
+  const int lane = lanes_per_out == 32 ? (threadIdx.x & 31) : 0;
+  const int shift = lanes_per_out == 32 ? 5 : 0;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> shift; i < total; i += ((int64_t)gridDim.x * blockDim.x) >> shift) {
     const int tap = (int)(i % 27);
     const int ci = (int)((i / 27) % Cin);
     const int co = (int)(i / (27 * (int64_t)Cin));
@@ -229,8 +231,8 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int sp
     const int mchunk = m / 64, mm = m % 64, qslab = nn / 16, nl = nn % 16;
     const float* src = partial + (((int64_t)qslab * mchunks + mchunk) * spatial) * stride + ((int64_t)mm * 27 + t) * 16 + nl;
     double s = 0.0;
-    for (int c = lane; c < spatial; c += 32) s += (double)src[(int64_t)c * stride];
-    s = warp_sum_d(s);
+    for (int c = lane; c < spatial; c += lanes_per_out) s += (double)src[(int64_t)c * stride];
+    if (lanes_per_out == 32) s = warp_sum_d(s);
     if (lane == 0) dw[i] = (float)s;
   }
 }
@@ -422,19 +424,21 @@ convt_wgrad_tc_kernel(const CtParams g, const __grid_constant__ CUtensorMap tm_x
 
 // partial[(qslab, mchunk, spatial)][m][child*16 + col] -> dw[ci][co][child]
 __global__ void convt_wgrad_tc_reduce_kernel(const float* __restrict__ partial, int spatial, int mchunks, int mrows, int Cin, int Cout,
-                                             float* __restrict__ dw) {
+                                             float* __restrict__ dw, int lanes_per_out) {
   const int64_t total = (int64_t)Cin * Cout * 8;
   const int64_t stride = (int64_t)mrows * 128;
-  const int lane = threadIdx.x & 31;
-  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < total; i += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+  // lanes_per_out = 32: one warp per output (many partials); 1: one thread per output (few partials, many outputs)
+  const int lane = lanes_per_out == 32 ? (threadIdx.x & 31) : 0;
+  const int shift = lanes_per_out == 32 ? 5 : 0;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> shift; i < total; i += ((int64_t)gridDim.x * blockDim.x) >> shift) {
     const int child = (int)(i % 8);
     const int co = (int)((i / 8) % Cout);
     const int ci = (int)(i / (8 * (int64_t)Cout));
     const int mchunk = ci / 64, mm = ci % 64, qslab = co / 16, cl = co % 16;
     const float* src = partial + (((int64_t)qslab * mchunks + mchunk) * spatial) * stride + (int64_t)mm * 128 + child * 16 + cl;
     double s = 0.0;
-    for (int c = lane; c < spatial; c += 32) s += (double)src[(int64_t)c * stride];
-    s = warp_sum_d(s);
+    for (int c = lane; c < spatial; c += lanes_per_out) s += (double)src[(int64_t)c * stride];
+    if (lanes_per_out == 32) s = warp_sum_d(s);
     if (lane == 0) dw[i] = (float)s;
   }
 }
@@ -490,8 +494,9 @@ int b200_convt2_wgrad_tc(const void* x, const void* gy, float* dw, void* workspa
   convt_wgrad_tc_kernel<<<grid, kCtThreads, pl.smem, stream>>>(g, tm_x);
   B200_CHECK_LAUNCH("convt2_wgrad_tc");
   const int64_t total = (int64_t)Cin * Cout * 8;
-  convt_wgrad_tc_reduce_kernel<<<b200_grid_for(total * 32, 256, B200_NUM_SMS * 16), 256, 0, stream>>>((const float*)workspace, pl.spatial, pl.mchunks,
-                                                                                                    pl.mrows, Cin, Cout, dw);
+  const int lpo = pl.spatial >= 64 ? 32 : 1;
+  convt_wgrad_tc_reduce_kernel<<<b200_grid_for(total * lpo, 256, B200_NUM_SMS * 16), 256, 0, stream>>>((const float*)workspace, pl.spatial, pl.mchunks,
+                                                                                                     pl.mrows, Cin, Cout, dw, lpo);
   B200_CHECK_LAUNCH("convt2_wgrad_tc_reduce");
   return B200_OK;
 }
@@ -547,8 +552,9 @@ int b200_conv3d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const v
   wgrad_tc_kernel<<<grid, kThreads, pl.smem, stream>>>(g, tm_p, tm_q0, tm_q1);
   B200_CHECK_LAUNCH("conv3d_wgrad_tc");
   const int64_t total = (int64_t)Cout * (c0 + c1) * 27;
-  wgrad_tc_reduce_kernel<<<b200_grid_for(total * 32, 256, B200_NUM_SMS * 16), 256, 0, stream>>>((const float*)workspace, pl.spatial, pl.mchunks, g.mrows,
-                                                                                        Cout, c0 + c1, pl.swapped, dw);
+  const int lpo = pl.spatial >= 64 ? 32 : 1;
+  wgrad_tc_reduce_kernel<<<b200_grid_for(total * lpo, 256, B200_NUM_SMS * 16), 256, 0, stream>>>((const float*)workspace, pl.spatial, pl.mchunks, g.mrows,
+                                                                                         Cout, c0 + c1, pl.swapped, dw, lpo);
   B200_CHECK_LAUNCH("conv3d_wgrad_tc_reduce");
   return B200_OK;
 }

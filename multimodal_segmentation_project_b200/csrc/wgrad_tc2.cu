@@ -221,11 +221,13 @@ wgrad_tc2_kernel(const Wg2Params g, const __grid_constant__ CUtensorMap tm_p, co
 
 // partial[(qslab, pgroup, spatial)][ps][ci 16][tap 27][co 16] -> dw[co][ci][27]
 __global__ void wgrad_tc2_reduce_kernel(const float* __restrict__ partial, int spatial, int pgroups, int pslabs, int Cout, int Cin,
-                                        float* __restrict__ dw) {
+                                        float* __restrict__ dw, int lanes_per_out) {
   const int64_t total = (int64_t)Cout * Cin * 27;
   const int64_t stride = (int64_t)pslabs * 16 * 27 * 16;
-  const int lane = threadIdx.x & 31;
-  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < total; i += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+  // lanes_per_out = 32: one warp per output (many partials); 1: one thread per output (few partials, many outputs)
+  const int lane = lanes_per_out == 32 ? (threadIdx.x & 31) : 0;
+  const int shift = lanes_per_out == 32 ? 5 : 0;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> shift; i < total; i += ((int64_t)gridDim.x * blockDim.x) >> shift) {
     const int tap = (int)(i % 27);
     const int ci = (int)((i / 27) % Cin);
     const int co = (int)(i / (27 * (int64_t)Cin));
@@ -233,8 +235,8 @@ __global__ void wgrad_tc2_reduce_kernel(const float* __restrict__ partial, int s
     const int pgroup = pslab / pslabs, ps = pslab % pslabs;
     const float* src = partial + (((int64_t)qslab * pgroups + pgroup) * spatial) * stride + (((int64_t)ps * 16 + cl) * 27 + tap) * 16 + col;
     double s = 0.0;
-    for (int c = lane; c < spatial; c += 32) s += (double)src[(int64_t)c * stride];
-    s = warp_sum_d(s);
+    for (int c = lane; c < spatial; c += lanes_per_out) s += (double)src[(int64_t)c * stride];
+    if (lanes_per_out == 32) s = warp_sum_d(s);
     if (lane == 0) dw[i] = (float)s;
   }
 }
@@ -299,8 +301,9 @@ int b200_conv3d_wgrad_tc2(const void* x0, int c0, const void* x1, int c1, const 
   wgrad_tc2_kernel<<<grid, kThreads, pl.smem, stream>>>(g, tm_p, tm_q0, tm_q1);
   B200_CHECK_LAUNCH("conv3d_wgrad_tc2");
   const int64_t total = (int64_t)Cout * (c0 + c1) * 27;
-  wgrad_tc2_reduce_kernel<<<b200_grid_for(total * 32, 256, B200_NUM_SMS * 16), 256, 0, stream>>>((const float*)workspace, pl.spatial, pl.pgroups,
-                                                                                               pl.pslabs, Cout, c0 + c1, dw);
+  const int lpo = pl.spatial >= 64 ? 32 : 1;
+  wgrad_tc2_reduce_kernel<<<b200_grid_for(total * lpo, 256, B200_NUM_SMS * 16), 256, 0, stream>>>((const float*)workspace, pl.spatial, pl.pgroups,
+                                                                                                pl.pslabs, Cout, c0 + c1, dw, lpo);
   B200_CHECK_LAUNCH("conv3d_wgrad_tc2_reduce");
   return B200_OK;
 }
