@@ -93,6 +93,9 @@ int64_t b200_pack_conv3_bytes(int mode, int dtype, int Cout, int Cin);
 /* resolves impl=0 (auto) for a given problem: returns 1 (CUDA-core, B200_PACK_FPROP/DGRAD weights) or
  * 2 (tcgen05, B200_PACK_*_TC weights); the caller packs the weights accordingly. */
 int b200_conv3d_k3_select(int dtype, int impl, int c0, int c1, int co0, int co1, int N, int D, int H, int W);
+/* selects the persistent tcgen05 convolution (one CTA per SM looping over tiles, double-buffered TMEM):
+ * 0 never, 1 auto (default), 2 whenever the layer has enough tiles — for tests and benchmarks. */
+int b200_set_conv_persistent(int mode);
 int b200_conv3d_k3(int dtype, int impl, const void* x0, int c0, const void* x1, int c1,
                    const void* wpack, const float* bias, void* y0, int co0, void* y1, int co1,
                    int N, int D, int H, int W, void* stream);
@@ -117,14 +120,15 @@ int64_t b200_bn_partials_bytes(int C);
 int b200_bn_stats(int dtype, const void* x, int64_t M, int C, float* partials, void* stream);
 /* training != 0: batch statistics (biased var for normalisation, unbiased for running_var,
  * momentum update, num_batches_tracked += 1); training == 0: running statistics.
- * Outputs scale[c] = gamma*invstd, shift[c] = beta - mean*scale, mean[c], invstd[c]. */
+ * Outputs scale[c] = gamma*invstd, shift[c] = beta, mean[c], invstd[c]; the apply kernels evaluate
+ * (x - mean)*scale + shift (the reference's order of operations: no cancellation when |mean| >> std). */
 int b200_bn_finalize(int dtype, const void* x, const float* partials, int64_t M, int C, const float* gamma, const float* beta,
                      float eps, float momentum, int training, float* running_mean, float* running_var,
                      int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* invstd,
                      void* stream);
-/* y = dropmask[n,c] * relu(x*scale[c] + shift[c]);  dropmask NULL = no dropout;
+/* y = dropmask[n,c] * relu((x - mean[c])*scale[c] + shift[c]);  dropmask NULL = no dropout;
  * x: [N, S, C] rows, y same. relu: 0/1. */
-int b200_bn_act_fwd(int dtype, const void* x, void* y, const float* scale, const float* shift,
+int b200_bn_act_fwd(int dtype, const void* x, void* y, const float* scale, const float* shift, const float* mean,
                     const float* dropmask, int relu, int64_t N, int64_t S, int C, void* stream);
 /* backward: g = gy * dropmask * [relu active]; partial sums of g and g*xhat */
 int b200_bn_act_bwd_reduce(int dtype, const void* gy, const void* x, const float* scale, const float* shift,

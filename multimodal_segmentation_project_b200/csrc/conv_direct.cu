@@ -511,6 +511,11 @@ bool b200_conv3d_k3_tc_supported(int c0, int c1, int co0, int co1, int N, int D,
 int b200_conv3d_k3_tc2(const void* x0, int c0, const void* x1, int c1, const void* wpack, const float* bias, void* y0,
                        int co0, void* y1, int co1, int N, int D, int H, int W, cudaStream_t stream);
 int b200_pack_conv3_weights_tc2(int mode, const float* w, void* out, int Cout, int Cin, cudaStream_t stream);
+// persistent variant for layers with many tiles (conv_tc3.cu); same packed weights as tc2
+bool b200_conv3d_k3_tc3_wanted(int c0, int c1, int co0, int co1, int N, int D, int H, int W);
+int b200_conv3d_k3_tc3(const void* x0, int c0, const void* x1, int c1, const void* wpack, const float* bias, void* y0,
+                       int co0, void* y1, int co1, int N, int D, int H, int W, cudaStream_t stream);
+static int g_conv_persistent = -1;  // -1 unset (env B200_CONV_PERSISTENT or 1), 0 never, 1 auto, 2 whenever the layer has enough tiles
 static int tc_version() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("B200_CONV_TC_VERSION"); v = e ? atoi(e) : 2; }
@@ -584,7 +589,16 @@ extern "C" int b200_conv3d_k3(int dtype, int impl, const void* x0, int c0, const
     B200_REQUIRE(dtype == B200_BF16, B200_ERR_UNSUPPORTED, "conv3d_k3: tcgen05 path is bf16 only");
     B200_REQUIRE(b200_conv3d_k3_tc_supported(c0, c1, co0, co1, N, D, H, W), B200_ERR_UNSUPPORTED,
                  "conv3d_k3(tcgen05): channels (%d+%d)->(%d+%d) need multiples of 16 (Cout <= 128 or a multiple of 128)", c0, c1, co0, co1);
-    if (tc_version() == 2) return b200_conv3d_k3_tc2(x0, c0, x1, c1, wpack, bias, y0, co0, y1, co1, N, D, H, W, st);
+    if (tc_version() == 2) {
+      // The persistent kernel (conv_tc3.cu) is within a few % of the two-CTA-per-SM kernel: both are bound by the
+      // tensor core's serialized operand fetch (T_mma ~ A wavefronts + B wavefronts + N/2).  It wins
+      // for single-slab 16-channel layers (2048 tiles, 120.9 vs 129.0 us at 2x128^3) and is used only there by default.
+      if (g_conv_persistent < 0) { const char* e = getenv("B200_CONV_PERSISTENT"); g_conv_persistent = e ? atoi(e) : 1; }
+      const bool want = g_conv_persistent == 2 || (g_conv_persistent == 1 && c0 + c1 == 16 && co0 + co1 == 16);
+      if (want && b200_conv3d_k3_tc3_wanted(c0, c1, co0, co1, N, D, H, W))
+        return b200_conv3d_k3_tc3(x0, c0, x1, c1, wpack, bias, y0, co0, y1, co1, N, D, H, W, st);
+      return b200_conv3d_k3_tc2(x0, c0, x1, c1, wpack, bias, y0, co0, y1, co1, N, D, H, W, st);
+    }
     return b200_conv3d_k3_tc(x0, c0, x1, c1, wpack, bias, y0, co0, y1, co1, N, D, H, W, st);
   }
   if (co1 == 0 && b200_conv_stem_supported(c0, c1, co0) && (dtype == B200_F32 || dtype == B200_BF16))
@@ -609,6 +623,12 @@ extern "C" int b200_conv3d_k3(int dtype, int impl, const void* x0, int c0, const
   if (dtype == B200_BF16) RUN(__nv_bfloat16);
 #undef RUN
   B200_FAIL(B200_ERR_UNSUPPORTED, "conv3d_k3: unknown dtype %d", dtype);
+}
+
+extern "C" int b200_set_conv_persistent(int mode) {
+  B200_REQUIRE(mode >= 0 && mode <= 2, B200_ERR_UNSUPPORTED, "set_conv_persistent: mode must be 0 (never), 1 (auto) or 2 (whenever possible)");
+  g_conv_persistent = mode;
+  return B200_OK;
 }
 
 extern "C" int b200_set_wgrad_impl(int impl) {

@@ -323,7 +323,7 @@ int b200_conv3d_k3_tc2(const void* x0, int c0, const void* x1, int c1, const voi
   p.n_tile = n_tile_for(cout);
   p.slabs = (c0 + c1) / 16;
   p.kd_per_mma = 3 * p.n_tile <= 256 ? 3 : 2;
-  { const char* e = getenv("B200_TC_REPEAT"); p.mma_repeat = e ? atoi(e) : 1; if (p.mma_repeat < 1) p.mma_repeat = 1; }
+  { const char* e = getenv("B200_TC_REPEAT"); p.mma_repeat = e ? atoi(e) : 1; if (p.mma_repeat < 0) p.mma_repeat = 0; }
   int dseg = 256 / (2 * p.n_tile);
   if (dseg > kMaxDseg) dseg = kMaxDseg;
   if (dseg < 1) dseg = 1;

@@ -172,7 +172,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, const T* 
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
   const float sc = g * invstd;
   scale[c] = sc;
-  shift[c] = b - mean * sc;
+  shift[c] = b;  // the affine offset; kernels evaluate (x - mean) * scale + shift, which does not cancel when |mean| >> std
   mean_out[c] = mean;
   invstd_out[c] = invstd;
 }
@@ -180,8 +180,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, const T* 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 bn_act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ scale,
-                  const float* __restrict__ shift, const float* __restrict__ dropmask, int relu, int64_t N, int64_t S,
-                  int C) {
+                  const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ dropmask, int relu,
+                  int64_t N, int64_t S, int C) {
   const int CV = C / 8;
   const int64_t total = N * S * CV;
 #pragma unroll 4
@@ -194,12 +194,14 @@ bn_act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __res
     v.get(f);
     const float4 s0 = *reinterpret_cast<const float4*>(scale + cv * 8), s1 = *reinterpret_cast<const float4*>(scale + cv * 8 + 4);
     const float4 h0 = *reinterpret_cast<const float4*>(shift + cv * 8), h1 = *reinterpret_cast<const float4*>(shift + cv * 8 + 4);
+    const float4 m0 = *reinterpret_cast<const float4*>(mean + cv * 8), m1 = *reinterpret_cast<const float4*>(mean + cv * 8 + 4);
     const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
     const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
     const float* dm = dropmask ? dropmask + (row / S) * C + cv * 8 : nullptr;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float t = to_f32<T>(from_f32<T>(fmaf(f[k], sc[k], sh[k])));  // BN output rounded to the activation dtype
+      float t = to_f32<T>(from_f32<T>(fmaf(f[k] - mu[k], sc[k], sh[k])));  // BN output rounded to the activation dtype
       if (relu) t = fmaxf(t, 0.f);
       if (dm) t *= dm[k];
       f[k] = t;
@@ -227,7 +229,7 @@ __device__ __forceinline__ void bn_bwd_elem(const T* __restrict__ gy, const T* _
     float gg = g[k];
     if (dm) gg *= dm[k];
     if (relu) {
-      const float pre = to_f32<T>(from_f32<T>(fmaf(fx[k], scale[c], shift[c])));
+      const float pre = to_f32<T>(from_f32<T>(fmaf(fx[k] - mean[c], scale[c], shift[c])));
       if (!(pre > 0.f)) gg = 0.f;
     }
     g[k] = gg;
@@ -647,13 +649,13 @@ extern "C" int b200_bn_finalize(int dtype, const void* x, const float* partials,
   return B200_OK;
 }
 
-extern "C" int b200_bn_act_fwd(int dtype, const void* x, void* y, const float* scale, const float* shift,
+extern "C" int b200_bn_act_fwd(int dtype, const void* x, void* y, const float* scale, const float* shift, const float* mean,
                                const float* dropmask, int relu, int64_t N, int64_t S, int C, void* stream) {
   int rc = check_rows("bn_act_fwd", N * S, C);
   if (rc) return rc;
-  B200_REQUIRE(x && y && scale && shift, B200_ERR_SHAPE, "bn_act_fwd: null pointer");
+  B200_REQUIRE(x && y && scale && shift && mean, B200_ERR_SHAPE, "bn_act_fwd: null pointer");
   B200_DISPATCH_DTYPE(dtype, T, (bn_act_fwd_kernel<T><<<ew_grid(N * S * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
-                                    (const T*)x, (T*)y, scale, shift, dropmask, relu, N, S, C)));
+                                    (const T*)x, (T*)y, scale, shift, mean, dropmask, relu, N, S, C)));
   B200_CHECK_LAUNCH("bn_act_fwd");
   return B200_OK;
 }

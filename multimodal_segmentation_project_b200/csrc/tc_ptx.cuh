@@ -8,6 +8,16 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully converged warp.  Role loops are executed by ALL lanes of their warp (warp-uniform control
+// flow keeps descriptors and addresses in uniform registers); only the asynchronous instruction itself is issued
+// under this predicate.  A plain `if (lane == 0)` around the whole loop makes every operand "divergent" for the
+// compiler, which then wraps each tcgen05.mma in an ELECT / R2UR / BRA.U.ANY waterfall (~100 cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));

@@ -156,6 +156,11 @@ def set_wgrad_impl(impl: int) -> None:
     check(_lib.load().b200_set_wgrad_impl(int(impl)), "set_wgrad_impl")
 
 
+def set_conv_persistent(mode: int) -> None:
+    """0 never, 1 auto, 2 whenever the layer has enough tiles (process-wide; tests and benchmarks)."""
+    check(_lib.load().b200_set_conv_persistent(int(mode)), "set_conv_persistent")
+
+
 def _bn_partials(C, device):
     L = _lib.load()
     return torch.empty(L.b200_bn_partials_bytes(C) // 4, dtype=torch.float32, device=device)
@@ -198,7 +203,7 @@ class _ConvBNAct(torch.autograd.Function):
         )
         y = torch.empty_like(conv_out)
         check(
-            L.b200_bn_act_fwd(_dt(conv_out), _ptr(conv_out), _ptr(y), _ptr(stats[0]), _ptr(stats[1]), _ptr(dropmask), 1, N, S,
+            L.b200_bn_act_fwd(_dt(conv_out), _ptr(conv_out), _ptr(y), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]), _ptr(dropmask), 1, N, S,
                               Cout, _stream()),
             "bn_act_fwd",
         )

@@ -572,11 +572,21 @@ TC_CASES = [
     (1, 3, 8, 8, 128, 0, 256, 0),
     (2, 3, 7, 10, 16, 16, 16, 0),
     (1, 17, 33, 18, 16, 0, 16, 0),
+    (2, 44, 64, 64, 16, 0, 16, 0),     # 2*6*16 = 352 tiles -> persistent kernel, last d-block ragged (44 = 5*8 + 4)
+    (1, 20, 96, 80, 16, 16, 32, 0),    # concat input, n_tile 32 (dseg 4), persistent
+    (1, 21, 80, 96, 32, 0, 16, 16),    # split output (dgrad style), 2 slabs, persistent
 ]
 
 
+@pytest.fixture(params=[0, 2], ids=["two-cta", "persistent"])
+def conv_kernel_mode(request):
+    F.set_conv_persistent(request.param)
+    yield request.param
+    F.set_conv_persistent(1)
+
+
 @pytest.mark.parametrize("case", TC_CASES)
-def test_conv3d_tcgen05_vs_oracle(cuda_dev, case):
+def test_conv3d_tcgen05_vs_oracle(cuda_dev, case, conv_kernel_mode):
     N, D, H, W, c0, c1, co0, co1 = case
     Cin, Cout = c0 + c1, co0 + co1
     gen = torch.Generator().manual_seed(7)

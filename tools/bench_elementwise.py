@@ -20,7 +20,7 @@ def t(fn, nbytes, name):
     print(f"{name:22s} {ms*1e3:7.1f} us  {nbytes/ms/1e6:7.0f} GB/s  ({nbytes/1e6:.0f} MB algorithmic)")
 B = x.numel() * 2
 t(lambda: check(L.b200_bn_stats(1, _ptr(x), N * S, C, _ptr(part), _stream())), B, "bn_stats")
-t(lambda: check(L.b200_bn_act_fwd(1, _ptr(x), _ptr(y), _ptr(stats[0]), _ptr(stats[1]), None, 1, N, S, C, _stream())), 2 * B, "bn_act_fwd")
+t(lambda: check(L.b200_bn_act_fwd(1, _ptr(x), _ptr(y), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]), None, 1, N, S, C, _stream())), 2 * B, "bn_act_fwd")
 t(lambda: check(L.b200_bn_act_bwd_reduce(1, _ptr(gy), _ptr(x), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]), _ptr(stats[3]), None, 1, N, S, C, _ptr(part), _stream())), 2 * B, "bn_act_bwd_reduce")
 t(lambda: check(L.b200_bn_act_bwd_apply(1, _ptr(gy), _ptr(x), _ptr(y), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]), _ptr(stats[3]), None, 1, _ptr(sums), 1, N, S, C, _stream())), 3 * B, "bn_act_bwd_apply")
 xp = torch.empty(N, 64, 64, 64, C, device=dev, dtype=torch.bfloat16)
