@@ -32,7 +32,7 @@ constexpr int kQStages = 3, kPStages = 4;   // P planes stay resident for three 
 constexpr int kThreads = 288;                        // 4 producer + 4 epilogue + 1 MMA warps
 constexpr int kHeader = 256;
 constexpr int kAccCols = 9 * 48;                     // 432 -> 512 allocated
-constexpr int kMaxDseg = 16;
+constexpr int kMaxDseg = 128;  // long d-runs: fewer split-K partials to reduce; ~2 CTA slots per SM are enough
 
 struct WgParams {
   const bf16* p; int cp;        // M-side tensor [N,D,H,W,cp]
@@ -254,7 +254,7 @@ WgPlan make_plan(int c0, int c1, int Cout, int N, int D, int H, int W) {
   // enough CTAs to fill the machine a few times, but long d-runs to amortise the 432-column epilogue
   const int64_t base = (int64_t)pl.tiles_w * pl.tiles_h * N * pl.mchunks * pl.qslabs;
   int dseg = kMaxDseg;
-  while (dseg > 2 && base * ((D + dseg - 1) / dseg) < 2 * B200_NUM_SMS) dseg >>= 1;
+  while (dseg > 2 && base * ((D + dseg - 1) / dseg) < (int64_t)(1.7 * B200_NUM_SMS)) dseg >>= 1;
   if (dseg > D) dseg = D;
   pl.dseg = dseg;
   pl.dblocks = (D + dseg - 1) / dseg;

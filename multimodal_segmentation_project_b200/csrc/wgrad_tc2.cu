@@ -31,7 +31,7 @@ constexpr int kPSlabBytes = 256 * 32;                // 16x16 voxels x 16 ch
 constexpr int kQStages = 3, kPStages = 4;            // a dY plane stays resident for three X planes (kd = 0,1,2)
 constexpr int kThreads = 256;                        // w0: TMA, w1: MMA, w2: TMEM alloc, w4-7: epilogue
 constexpr int kHeader = 256;
-constexpr int kMaxDseg = 16;
+constexpr int kMaxDseg = 128;  // long d-runs: fewer split-K partials to reduce; ~2 CTA slots per SM are enough
 
 struct Wg2Params {
   float* partial;               // [cta][pslab (<=2)][ci 16][27][co 16]
@@ -255,7 +255,7 @@ Wg2Plan make_plan(int c0, int c1, int Cout, int N, int D, int H, int W) {
   pl.tiles_h = (H + 15) / 16;
   const int64_t base = (int64_t)pl.tiles_w * pl.tiles_h * N * pl.pgroups * pl.qslabs;
   int dseg = kMaxDseg;
-  while (dseg > 2 && base * ((D + dseg - 1) / dseg) < 2 * B200_NUM_SMS) dseg >>= 1;
+  while (dseg > 2 && base * ((D + dseg - 1) / dseg) < (int64_t)(1.7 * B200_NUM_SMS)) dseg >>= 1;
   if (dseg > D) dseg = D;
   pl.dseg = dseg;
   pl.dblocks = (D + dseg - 1) / dseg;
