@@ -536,6 +536,15 @@ static int wg_version() {
   if (v < 0) { const char* e = getenv("B200_WGRAD_TC_VERSION"); v = e ? atoi(e) : 2; }
   return v;
 }
+// ConvTranspose3d forward / data gradient on the tensor cores (convt_tc.cu)
+bool b200_convt2_tc_supported(int Cin, int Cout);
+int b200_convt2_fwd_tc(const void* x, const float* w, const float* bias, void* y, int N, int D, int H, int W, int Cin, int Cout, cudaStream_t st);
+int b200_convt2_bwd_data_tc(const void* gy, const float* w, void* gx, int N, int D, int H, int W, int Cin, int Cout, cudaStream_t st);
+static int convt_tc_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200_CONVT_TC"); v = e ? atoi(e) : 1; }
+  return v;
+}
 bool b200_convt2_wgrad_tc_supported(int Cin, int Cout, int N, int D, int H, int W);
 int64_t b200_convt2_wgrad_tc_workspace(int Cin, int Cout, int N, int D, int H, int W);
 int b200_convt2_wgrad_tc(const void* x, const void* gy, float* dw, void* workspace, int N, int D, int H, int W, int Cin, int Cout, cudaStream_t stream);
@@ -706,6 +715,8 @@ extern "C" int b200_convt2_fwd(int dtype, const void* x, const float* w, const f
                                int W, int Cin, int Cout, void* stream) {
   B200_REQUIRE(x && w && y && N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, B200_ERR_SHAPE, "convt2_fwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200_BF16 && convt_tc_enabled() && b200_convt2_tc_supported(Cin, Cout))
+    return b200_convt2_fwd_tc(x, w, bias, y, N, D, H, W, Cin, Cout, st);
   const Geom g{N, D, H, W};
   const bool avec = Cin % 8 == 0, ovec = Cout % 8 == 0;
 #define RUN(T)                                                                                             \
@@ -728,6 +739,8 @@ extern "C" int b200_convt2_bwd_data(int dtype, const void* gy, const float* w, v
                                     int Cout, void* stream) {
   B200_REQUIRE(gy && w && gx && N > 0 && D > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, B200_ERR_SHAPE, "convt2_bwd_data: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200_BF16 && convt_tc_enabled() && b200_convt2_tc_supported(Cin, Cout))
+    return b200_convt2_bwd_data_tc(gy, w, gx, N, D, H, W, Cin, Cout, st);
   const Geom g{N, D, H, W};
   const bool avec = Cout % 8 == 0, ovec = Cin % 8 == 0;
 #define RUN(T)                                                                                               \

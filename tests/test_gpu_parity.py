@@ -267,9 +267,10 @@ def test_maxpool_fwd_bwd(cuda_dev, dtype, shape):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_conv_transpose_fwd_bwd(cuda_dev, dtype):
+@pytest.mark.parametrize("shape", [(2, 32, 16, 3, 4, 5), (1, 256, 128, 2, 2, 2), (1, 64, 32, 5, 17, 20), (2, 128, 64, 3, 16, 9)])
+def test_conv_transpose_fwd_bwd(cuda_dev, dtype, shape):
     gen = torch.Generator().manual_seed(2)
-    N, Cin, Cout, D, H, W = 2, 32, 16, 3, 4, 5
+    N, Cin, Cout, D, H, W = shape
     x = torch.randn(N, Cin, D, H, W, generator=gen).to(dtype).float()
     w = (torch.randn(Cin, Cout, 2, 2, 2, generator=gen) / Cin ** 0.5)
     b = torch.randn(Cout, generator=gen)
