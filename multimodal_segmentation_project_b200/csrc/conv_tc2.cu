@@ -40,6 +40,9 @@ struct Tc2Params {
   int n_tile, dseg, dblocks, slabs, wstages, tmem_cols, tiles_w, stages;
   int kd_per_mma;   // 3 when 3*n_tile <= 256, else 2 (n_tile = 128)
   int mma_repeat;   // diagnostics only (B200_TC_REPEAT): issue the fused MMAs this many times
+  int ksplit;       // > 1: this CTA reduces only slabs [zs*slabs_per, ...) and writes fp32 partials (deep layers: few tiles, many slabs)
+  int slabs_per;
+  float* partial;   // [ksplit][rows][cout]
 };
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, int c, int w, int h, int d, int n, uint32_t bar) {
@@ -82,11 +85,13 @@ conv3d_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tm0, co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tw = blockIdx.x % p.tiles_w, th = blockIdx.x / p.tiles_w;
   const int n = blockIdx.y / p.dblocks, db = blockIdx.y % p.dblocks;
-  const int nchunk = blockIdx.z;
+  const int nchunk = blockIdx.z / p.ksplit, zs = blockIdx.z % p.ksplit;
+  const int slab0 = zs * p.slabs_per;
+  const int nslabs = min(p.slabs_per, p.slabs - slab0);
   const int w0 = tw * 16, h0 = th * 16, d0 = db * p.dseg;
   const int planes = min(p.dseg, p.D - d0);
   const int nq = planes + 2;
-  const int total_stages = p.slabs * nq;
+  const int total_stages = nslabs * nq;
   const uint32_t wbytes = 864u * p.n_tile;
 
   if (warp == 2 && lane == 0) {
@@ -103,7 +108,7 @@ conv3d_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tm0, co
     prefetch_tmap(&tm0);
     if (p.c1) prefetch_tmap(&tm1);
   }
-  if (warp >= 4 && threadIdx.x - 128 < p.n_tile) bias_s[threadIdx.x - 128] = p.bias ? p.bias[blockIdx.z * p.n_tile + (threadIdx.x - 128)] : 0.f;
+  if (warp >= 4 && threadIdx.x - 128 < p.n_tile) bias_s[threadIdx.x - 128] = p.bias ? p.bias[(blockIdx.z / p.ksplit) * p.n_tile + (threadIdx.x - 128)] : 0.f;
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -117,7 +122,7 @@ conv3d_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tm0, co
         const int st = it % p.stages;
         tc::mbar_wait(a_empty(st), ((it / p.stages) & 1) ^ 1);
         tc::mbar_arrive_expect_tx(a_full(st), kStageTx);
-        const int c = s * 16;
+        const int c = (slab0 + s) * 16;
         const CUtensorMap* tm = c < p.c0 ? &tm0 : &tm1;
         const int cc = c < p.c0 ? c : c - p.c0;
         const uint32_t dst = tc::smem_u32(act + st * kStageBytes);
@@ -127,11 +132,11 @@ conv3d_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tm0, co
   } else if (warp == 1) {
     // ===================== weight slabs by TMA bulk copy =====================
     if (lane == 0) {
-      for (int s = 0; s < p.slabs; ++s) {
+      for (int s = 0; s < nslabs; ++s) {
         const int ws = s % p.wstages;
         tc::mbar_wait(w_empty(ws), ((s / p.wstages) & 1) ^ 1);
         tc::mbar_arrive_expect_tx(w_full(ws), wbytes);
-        tc::bulk_g2s(tc::smem_u32(wts + (size_t)ws * wbytes), p.wpack + ((size_t)nchunk * p.slabs + s) * wbytes, wbytes, w_full(ws));
+        tc::bulk_g2s(tc::smem_u32(wts + (size_t)ws * wbytes), p.wpack + ((size_t)nchunk * p.slabs + slab0 + s) * wbytes, wbytes, w_full(ws));
       }
     }
   } else if (warp == 2) {
@@ -151,7 +156,7 @@ conv3d_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tm0, co
       for (int i = 1; i <= 3; ++i) idesc_n[i] = tc::idesc_bf16_f32(128, (int)(i * n_t));
       const bool wt1 = w0 + 8 < p.W;
       const uint32_t wt_cols = (uint32_t)p.dseg * n_t;
-      for (int s = 0; s < p.slabs; ++s) {
+      for (int s = 0; s < nslabs; ++s) {
         const int ws = s % p.wstages;
         tc::mbar_wait(w_full(ws), (s / p.wstages) & 1);
         tc::tc_fence_after();
@@ -196,7 +201,7 @@ conv3d_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tm0, co
             }
           }
           tc::umma_commit(a_empty(st));
-          if (s == p.slabs - 1 && q >= 1) tc::umma_commit(acc_full(q - 1));
+          if (s == nslabs - 1 && q >= 1) tc::umma_commit(acc_full(q - 1));
         }
         tc::umma_commit(w_empty(ws));
       }
@@ -220,6 +225,15 @@ conv3d_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tm0, co
           tc::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + col0 + cc * 16, r);
           tc::tmem_ld_wait();
           const int ch = nchunk * p.n_tile + cc * 16;
+          if (p.ksplit > 1) {
+            if (valid) {
+              float4* dst = reinterpret_cast<float4*>(p.partial + ((int64_t)zs * p.N * p.D * p.H * p.W + row) * (p.co0 + p.co1) + ch);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+            }
+            continue;
+          }
           uint32_t packed[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -265,6 +279,40 @@ __global__ void pack_k3_tc2_kernel(const float* __restrict__ w, bf16* __restrict
 }
 
 inline int n_tile_for(int cout) { return cout <= 128 ? cout : 128; }
+
+// split-K epilogue: y = bf16(sum_z partial[z] + bias), channels [0,co0) -> y0, [co0, co0+co1) -> y1
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int ksplit, int64_t rows, int cout, const float* __restrict__ bias,
+                                     bf16* __restrict__ y0, bf16* __restrict__ y1, int co0, int co1) {
+  const int CV = cout / 8;
+  const int64_t total = rows * CV;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    const int64_t row = i / CV;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = bias ? bias[cv * 8 + k] : 0.f;
+    for (int z = 0; z < ksplit; ++z) {
+      const float4* src = reinterpret_cast<const float4*>(partial + ((int64_t)z * rows + row) * cout + cv * 8);
+      const float4 a = src[0], b = src[1];
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    Vec8<bf16> v;
+    v.set(acc);
+    const int ch = cv * 8;
+    if (ch < co0) v.store(y0 + row * co0 + ch); else v.store(y1 + row * co1 + (ch - co0));
+  }
+}
+
+float* splitk_scratch(size_t bytes) {
+  static float* buf = nullptr;
+  static size_t cap = 0;
+  if (cap < bytes) {
+    if (buf) cudaFree(buf);
+    if (cudaMalloc(&buf, bytes) != cudaSuccess) { buf = nullptr; cap = 0; return nullptr; }
+    cap = bytes;
+  }
+  return buf;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -355,8 +403,29 @@ int b200_conv3d_k3_tc2(const void* x0, int c0, const void* x1, int c1, const voi
     B200_CUDA(cudaFuncSetAttribute(conv3d_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  dim3 grid((unsigned)(p.tiles_w * tiles_h), (unsigned)(N * p.dblocks), (unsigned)(cout / p.n_tile));
+  // deep layers: few output tiles but many channel slabs -> split the reduction over CTAs (fp32 partials + one reduce pass)
+  p.ksplit = 1; p.slabs_per = p.slabs; p.partial = nullptr;
+  const int64_t ctas = (int64_t)p.tiles_w * tiles_h * N * p.dblocks * (cout / p.n_tile);
+  static int splitk_enabled = -1;
+  if (splitk_enabled < 0) { const char* e = getenv("B200_CONV_SPLITK"); splitk_enabled = e ? atoi(e) : 1; }
+  if (splitk_enabled && ctas * 2 <= B200_NUM_SMS && p.slabs >= 4) {
+    int want = (int)((2 * B200_NUM_SMS + ctas - 1) / ctas);
+    if (want > p.slabs) want = p.slabs;
+    p.slabs_per = (p.slabs + want - 1) / want;
+    p.ksplit = (p.slabs + p.slabs_per - 1) / p.slabs_per;
+    if (p.ksplit > 1) {
+      const size_t bytes = (size_t)p.ksplit * N * D * H * W * cout * sizeof(float);
+      p.partial = splitk_scratch(bytes);
+      B200_REQUIRE(p.partial != nullptr, B200_ERR_CUDA, "conv3d_k3(tcgen05): could not allocate the split-K scratch buffer (%zu bytes)", bytes);
+    } else { p.slabs_per = p.slabs; }
+  }
+  dim3 grid((unsigned)(p.tiles_w * tiles_h), (unsigned)(N * p.dblocks), (unsigned)(cout / p.n_tile * p.ksplit));
   conv3d_tc2_kernel<<<grid, kThreads, smem, stream>>>(p, tm0, tm1);
   B200_CHECK_LAUNCH("conv3d_k3_tc2");
+  if (p.ksplit > 1) {
+    const int64_t rows = (int64_t)N * D * H * W;
+    splitk_reduce_kernel<<<b200_grid_for(rows * (cout / 8), 256, B200_NUM_SMS * 8), 256, 0, stream>>>(p.partial, p.ksplit, rows, cout, bias, p.y0, p.y1, co0, co1);
+    B200_CHECK_LAUNCH("conv3d_k3_tc2_splitk_reduce");
+  }
   return B200_OK;
 }
