@@ -59,6 +59,9 @@ class FlatParams:
                 cands = [p for n, p in late if n == want]
                 self.early_sentinel = cands[0] if cands else None
 
+        self._views = [self.grad[o:o + k].view_as(p) for (n, p), (o, k) in zip(self.order, (self.offsets[n] for n, _ in self.order))]
+        self.n_early_params = len(early)
+
     def buckets(self):
         if self.n_early in (0, self.total):
             return [self.grad]
@@ -66,6 +69,25 @@ class FlatParams:
 
     def zero_grad(self):
         self.grad.zero_()
+
+    # ---- "detached gradient" mode: autograd stores every parameter gradient as its own tensor (p.grad starts as
+    # None, so AccumulateGrad keeps the tensor the kernels produced instead of launching one add per parameter), and the
+    # gradients are gathered into the flat buffer by one multi-tensor copy per bucket.
+    def detach_grads(self):
+        for _, p in self.order:
+            p.grad = None
+
+    def gather_grads(self, which="all"):
+        lo, hi = {"all": (0, len(self.order)), "early": (0, self.n_early_params), "late": (self.n_early_params, len(self.order))}[which]
+        dst, src = [], []
+        for (n, p), v in zip(self.order[lo:hi], self._views[lo:hi]):
+            if p.grad is None:
+                v.zero_()
+            else:
+                dst.append(v)
+                src.append(p.grad)
+        if dst:
+            torch._foreach_copy_(dst, src)
 
 
 class DataParallelTrainer:
@@ -99,6 +121,7 @@ class DataParallelTrainer:
     def _early_hook(self, _param):
         # called by autograd right after the sentinel's gradient was accumulated: everything in the
         # early bucket is final -> reduce it on the side stream while the encoder backward continues
+        self.fp.gather_grads("early")
         cur = torch.cuda.current_stream()
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
@@ -106,7 +129,12 @@ class DataParallelTrainer:
         self._early_done = True
 
     def allreduce_grads(self):
+        if self.overlap and self._early_done:
+            self.fp.gather_grads("late")
+        else:
+            self.fp.gather_grads("all")
         if self.world == 1:
+            self._early_done = False
             return
         b = self.fp.buckets()
         if self.overlap and self._early_done:
@@ -119,7 +147,7 @@ class DataParallelTrainer:
 
     # -- one training step -------------------------------------------------------------------------
     def _step_impl(self, x, y):
-        self.fp.zero_grad()
+        self.fp.detach_grads()
         if self.autocast_dtype is not None and x.is_cuda:
             with torch.autocast("cuda", dtype=self.autocast_dtype):
                 out = self.model(x)
