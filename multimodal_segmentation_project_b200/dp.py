@@ -114,6 +114,8 @@ class DataParallelTrainer:
             self.fp.early_sentinel.register_post_accumulate_grad_hook(self._early_hook)
         self.graph = None
         self.static_x = self.static_y = None
+        self._copy_stream = None
+        self._stage = None
         self.loss = None
         self.metrics = None
 
@@ -189,5 +191,35 @@ class DataParallelTrainer:
             self.static_x.copy_(x, non_blocking=True)
         if y is not None:
             self.static_y.copy_(y, non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+    # -- input pipeline: the next batch crosses PCIe while the current step computes -----------------
+    def prefetch(self, x_host, y_host):
+        """Starts the host -> device copy of the NEXT step's batch (pinned host tensors) on a copy stream.
+        The batch lands in a staging pair; replay_prefetched() consumes it.  One batch in flight at a time."""
+        if self.graph is None:
+            raise RuntimeError("prefetch() needs a captured step: call capture() first")
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.static_x.device)
+            self._stage = (torch.empty_like(self.static_x), torch.empty_like(self.static_y))
+            self._stage_ready, self._stage_free = torch.cuda.Event(), torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream())
+        cs = self._copy_stream
+        cs.wait_event(self._stage_free)  # the previous consumer has read the staging pair
+        with torch.cuda.stream(cs):
+            self._stage[0].copy_(x_host, non_blocking=True)
+            self._stage[1].copy_(y_host, non_blocking=True)
+            self._stage_ready.record(cs)
+
+    def replay_prefetched(self):
+        """Runs the captured step on the batch staged by the last prefetch()."""
+        if self._stage is None:
+            raise RuntimeError("replay_prefetched() without a prefetch()")
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._stage_ready)
+        self.static_x.copy_(self._stage[0])
+        self.static_y.copy_(self._stage[1])
+        self._stage_free.record(cur)
         self.graph.replay()
         return self.loss

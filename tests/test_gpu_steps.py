@@ -199,3 +199,19 @@ def test_dp_trainer_single_gpu_matches_manual_step(cuda_dev):
     l1 = tr.replay().item()
     l2 = tr.replay(xc, yc).item()
     assert np.isfinite(l1) and np.isfinite(l2) and l2 < loss.item() + 1.0
+    # input pipeline: a prefetched batch (pinned host -> staging on a copy stream) feeds the same step as replay(x, y)
+    net2 = UNet3D(1, 4, dropout_rate=0.0).cuda(); net2.load_state_dict(sd); net2.train()
+    net3 = UNet3D(1, 4, dropout_rate=0.0).cuda(); net3.load_state_dict(sd); net3.train()
+    ta = DataParallelTrainer(net2, M.combined_loss, autocast_dtype=None); ta.capture(xc, yc, warmup=1)
+    tb = DataParallelTrainer(net3, M.combined_loss, autocast_dtype=None); tb.capture(xc, yc, warmup=1)
+    x2, y2 = structured_volume(2, 16, seed=77)
+    xh, yh = x2.pin_memory(), y2.pin_memory()
+    tb.prefetch(xh, yh)
+    for i in range(3):
+        la = ta.replay(xh, yh).item()
+        lb_t = tb.replay_prefetched()
+        if i < 2:
+            tb.prefetch(xh, yh)
+        assert la == lb_t.item()
+    with pytest.raises(RuntimeError):
+        DataParallelTrainer(UNet3D(1, 4).cuda(), M.combined_loss).prefetch(xh, yh)

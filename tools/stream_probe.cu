@@ -1,0 +1,291 @@
+// stream_probe.cu — which launch shape gets an elementwise bf16 pass (BatchNorm apply / BatchNorm statistics) closest to
+// the HBM roofline on B200?  Standalone: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o stream_probe stream_probe.cu
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <vector>
+#include <algorithm>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
+
+struct __align__(16) V16 { uint32_t w[4]; };
+struct __align__(32) V32 { uint32_t w[8]; };
+
+__device__ __forceinline__ V16 ld16(const void* p) { return *reinterpret_cast<const V16*>(p); }
+__device__ __forceinline__ void st16(void* p, V16 v) { *reinterpret_cast<V16*>(p) = v; }
+__device__ __forceinline__ V16 ld16_stream(const void* p) {
+  V16 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st16_stream(void* p, V16 v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]) : "memory");
+}
+__device__ __forceinline__ V32 ld32(const void* p) {
+  V32 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]), "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7])
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st32(void* p, V32 v) {
+  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]), "r"(v.w[4]),
+               "r"(v.w[5]), "r"(v.w[6]), "r"(v.w[7])
+               : "memory");
+}
+
+// BN apply on one 32-bit word (2 bf16): channel pair index cp
+__device__ __forceinline__ uint32_t bn2(uint32_t w, const float* __restrict__ mean, const float* __restrict__ scale, const float* __restrict__ shift, int c) {
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&w);
+  float2 f = __bfloat1622float2(b);
+  f.x = fmaxf(fmaf(f.x - mean[c], scale[c], shift[c]), 0.f);
+  f.y = fmaxf(fmaf(f.y - mean[c + 1], scale[c + 1], shift[c + 1]), 0.f);
+  __nv_bfloat162 o = __floats2bfloat162_rn(f.x, f.y);
+  return *reinterpret_cast<uint32_t*>(&o);
+}
+template <int NW, typename V>
+__device__ __forceinline__ V bnv(V v, const float* mean, const float* scale, const float* shift, int c0) {
+#pragma unroll
+  for (int i = 0; i < NW; ++i) v.w[i] = bn2(v.w[i], mean, scale, shift, c0 + 2 * i);
+  return v;
+}
+
+// (a) the shape in the library today: grid-stride, 16-B accesses, #pragma unroll 4
+__global__ void __launch_bounds__(256) apply_gs(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                                const float* __restrict__ scale, const float* __restrict__ shift, int64_t nvec, int C) {
+  const int CV = C / 8;
+#pragma unroll 4
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    V16 v = ld16(x + i * 8);
+    v = bnv<4>(v, mean, scale, shift, cv * 8);
+    st16(y + i * 8, v);
+  }
+}
+// (b) tile per block: U independent 16-B loads per thread issued first, then math, then stores
+template <int U, bool STREAM>
+__global__ void __launch_bounds__(256) apply_tile(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                                  const float* __restrict__ scale, const float* __restrict__ shift, int64_t nvec, int C) {
+  const int CV = C / 8;
+  for (int64_t base = (int64_t)blockIdx.x * (256 * U); base < nvec; base += (int64_t)gridDim.x * (256 * U)) {
+    V16 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + u * 256 + threadIdx.x;
+      if (i < nvec) v[u] = STREAM ? ld16_stream(x + i * 8) : ld16(x + i * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + u * 256 + threadIdx.x;
+      if (i < nvec) {
+        const int cv = (int)(i % CV);
+        V16 o = bnv<4>(v[u], mean, scale, shift, cv * 8);
+        if (STREAM) st16_stream(y + i * 8, o); else st16(y + i * 8, o);
+      }
+    }
+  }
+}
+// (c) 32-byte accesses (C % 16 == 0)
+template <int U>
+__global__ void __launch_bounds__(256) apply_tile32(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                                    const float* __restrict__ scale, const float* __restrict__ shift, int64_t nvec32, int C) {
+  const int CV = C / 16;
+  for (int64_t base = (int64_t)blockIdx.x * (256 * U); base < nvec32; base += (int64_t)gridDim.x * (256 * U)) {
+    V32 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + u * 256 + threadIdx.x;
+      if (i < nvec32) v[u] = ld32(x + i * 16);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + u * 256 + threadIdx.x;
+      if (i < nvec32) {
+        const int cv = (int)(i % CV);
+        st32(y + i * 16, bnv<8>(v[u], mean, scale, shift, cv * 16));
+      }
+    }
+  }
+}
+
+// statistics: per-thread shifted sums over 8 channels; (a) today's shape: grid-stride unroll 4; (b) U loads batched
+template <int U, bool STREAM>
+__global__ void __launch_bounds__(256) stats_tile(const __nv_bfloat16* __restrict__ x, int64_t nvec, int C, float* __restrict__ partials) {
+  float a0[8], a1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
+  // 256 % CV == 0 -> a thread always sees the same channel group
+  for (int64_t base = (int64_t)blockIdx.x * (256 * U); base < nvec; base += (int64_t)gridDim.x * (256 * U)) {
+    V16 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = base + u * 256 + threadIdx.x;
+      if (i < nvec) v[u] = STREAM ? ld16_stream(x + i * 8) : ld16(x + i * 8);
+      else v[u] = V16{{0, 0, 0, 0}};
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v[u].w[w]));
+        a0[2 * w] += f.x; a1[2 * w] = fmaf(f.x, f.x, a1[2 * w]);
+        a0[2 * w + 1] += f.y; a1[2 * w + 1] = fmaf(f.y, f.y, a1[2 * w + 1]);
+      }
+  }
+  __shared__ float sred[256 * 16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sred[threadIdx.x * 16 + i] = a0[i]; sred[threadIdx.x * 16 + 8 + i] = a1[i]; }
+  __syncthreads();
+  const int CV = C / 8;
+  for (int q = threadIdx.x; q < 2 * C; q += 256) {
+    const int slot = q / C, c = q % C, cv = c / 8, k = c % 8;
+    float t = 0.f;
+    for (int r = cv; r < 256; r += CV) t += sred[r * 16 + slot * 8 + k];
+    partials[(int64_t)blockIdx.x * 2 * C + q] = t;
+  }
+}
+
+// thread-constant channel group: (gridDim * 256) % CV == 0, so i % CV == threadIdx.x % CV for the whole loop
+template <int UNR>
+__global__ void __launch_bounds__(256) apply_hoist(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                                   const float* __restrict__ scale, const float* __restrict__ shift, int64_t nvec, int C) {
+  const int CV = C / 8, cv = threadIdx.x % CV;
+  float m[8], s[8], h[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { m[k] = mean[cv * 8 + k]; s[k] = scale[cv * 8 + k]; h[k] = shift[cv * 8 + k]; }
+#pragma unroll UNR
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    V16 v = ld16(x + i * 8);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v.w[w]));
+      f.x = fmaxf(fmaf(f.x - m[2 * w], s[2 * w], h[2 * w]), 0.f);
+      f.y = fmaxf(fmaf(f.y - m[2 * w + 1], s[2 * w + 1], h[2 * w + 1]), 0.f);
+      __nv_bfloat162 o = __floats2bfloat162_rn(f.x, f.y);
+      v.w[w] = *reinterpret_cast<uint32_t*>(&o);
+    }
+    st16(y + i * 8, v);
+  }
+}
+// params staged in shared memory once per block
+__global__ void __launch_bounds__(256) apply_smem(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                                  const float* __restrict__ scale, const float* __restrict__ shift, int64_t nvec, int C) {
+  __shared__ float sp[3 * 256];
+  for (int c = threadIdx.x; c < C; c += 256) { sp[c] = mean[c]; sp[256 + c] = scale[c]; sp[512 + c] = shift[c]; }
+  __syncthreads();
+  const int CV = C / 8, cv = threadIdx.x % CV;
+  const float *m = sp + cv * 8, *s = sp + 256 + cv * 8, *h = sp + 512 + cv * 8;
+#pragma unroll 4
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    V16 v = ld16(x + i * 8);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v.w[w]));
+      f.x = fmaxf(fmaf(f.x - m[2 * w], s[2 * w], h[2 * w]), 0.f);
+      f.y = fmaxf(fmaf(f.y - m[2 * w + 1], s[2 * w + 1], h[2 * w + 1]), 0.f);
+      __nv_bfloat162 o = __floats2bfloat162_rn(f.x, f.y);
+      v.w[w] = *reinterpret_cast<uint32_t*>(&o);
+    }
+    st16(y + i * 8, v);
+  }
+}
+__global__ void read_flush(const uint4* __restrict__ p, int64_t n, uint32_t* out) {
+  uint32_t a = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) { uint4 v = p[i]; a ^= v.x ^ v.y ^ v.z ^ v.w; }
+  if (a == 0x12345678u) *out = a;
+}
+extern "C" {
+int b200_bn_stats(int dtype, const void* x, int64_t M, int C, float* partials, void* stream);
+int b200_bn_act_fwd(int dtype, const void* x, void* y, const float* scale, const float* shift, const float* mean, const float* dropmask, int relu,
+                    int64_t N, int64_t S, int C, void* stream);
+int b200_bn_act_bwd_reduce(int dtype, const void* gy, const void* x, const float* scale, const float* shift, const float* mean, const float* invstd,
+                           const float* dropmask, int relu, int64_t N, int64_t S, int C, float* partials, void* stream);
+int b200_bn_act_bwd_apply(int dtype, const void* gy, const void* x, void* dx, const float* scale, const float* shift, const float* mean,
+                          const float* invstd, const float* dropmask, int relu, const float* sums, int training, int64_t N, int64_t S, int C, void* stream);
+}
+static bool g_read_flush = false;
+static uint32_t* g_sink = nullptr;
+
+template <typename F>
+static float time_it(F&& launch, void* flush, size_t flush_bytes, int iters = 7) {
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  std::vector<float> ts;
+  launch();
+  cudaDeviceSynchronize();
+  for (int i = 0; i < iters; ++i) {
+    if (g_read_flush) read_flush<<<148 * 8, 256>>>((const uint4*)flush, (int64_t)(flush_bytes / 16), g_sink);
+    else cudaMemsetAsync(flush, i, flush_bytes);
+    cudaEventRecord(a); launch(); cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    ts.push_back(ms);
+  }
+  std::sort(ts.begin(), ts.end());
+  return ts[ts.size() / 2];
+}
+
+int main(int argc, char** argv) {
+  g_read_flush = argc > 1 && argv[1][0] == 'r';
+  printf("flush: %s\n", g_read_flush ? "read 512 MB (clean L2 lines)" : "memset 512 MB (dirty L2 lines)");
+  const int C = 16;
+  const int64_t elems = 2LL * 128 * 128 * 128 * C;  // 67.1 M bf16 = 134 MB
+  const int64_t nvec = elems / 8;
+  __nv_bfloat16 *x, *y; float *par, *partials; void* flush;
+  const size_t flush_bytes = 512u << 20;
+  CK(cudaMalloc(&x, elems * 2)); CK(cudaMalloc(&y, elems * 2)); CK(cudaMalloc(&par, 3 * 256 * 4)); CK(cudaMalloc(&partials, 65536 * 2 * C * 4));
+  CK(cudaMalloc(&flush, flush_bytes)); CK(cudaMalloc(&g_sink, 4)); CK(cudaMemset(flush, 1, flush_bytes));
+  __nv_bfloat16* gy; CK(cudaMalloc(&gy, elems * 2)); CK(cudaMemset(gy, 0x3b, elems * 2));
+  CK(cudaMemset(x, 0x3c, elems * 2)); CK(cudaMemset(par, 0, 3 * 256 * 4));
+  float *mean = par, *scale = par + 256, *shift = par + 512;
+  const double rw = elems * 4.0 / 1e9, ro = elems * 2.0 / 1e9;  // GB
+  auto report = [&](const char* name, int grid, float ms, double gb) { printf("%-34s grid %6d  %7.1f us  %6.0f GB/s\n", name, grid, ms * 1e3, gb / (ms * 1e-3)); };
+  const int64_t S = 128LL * 128 * 128;
+  report("LIB b200_bn_act_fwd", 0, time_it([&] { b200_bn_act_fwd(1, x, y, scale, shift, mean, nullptr, 1, 2, S, C, nullptr); }, flush, flush_bytes), rw);
+  report("LIB b200_bn_stats", 0, time_it([&] { b200_bn_stats(1, x, 2 * S, C, partials, nullptr); }, flush, flush_bytes), ro);
+  report("LIB b200_bn_act_bwd_reduce", 0, time_it([&] { b200_bn_act_bwd_reduce(1, gy, x, scale, shift, mean, scale, nullptr, 1, 2, S, C, partials, nullptr); }, flush, flush_bytes), rw);
+  report("LIB b200_bn_act_bwd_apply", 0, time_it([&] { b200_bn_act_bwd_apply(1, gy, x, y, scale, shift, mean, scale, nullptr, 1, mean, 1, 2, S, C, nullptr); }, flush, flush_bytes), rw * 1.5);
+  for (int mult : {4, 8, 16}) {
+    const int g = 148 * mult;
+    report("apply hoist unroll4", g, time_it([&] { apply_hoist<4><<<g, 256>>>(x, y, mean, scale, shift, nvec, C); }, flush, flush_bytes), rw);
+    report("apply hoist unroll8", g, time_it([&] { apply_hoist<8><<<g, 256>>>(x, y, mean, scale, shift, nvec, C); }, flush, flush_bytes), rw);
+    report("apply smem params", g, time_it([&] { apply_smem<<<g, 256>>>(x, y, mean, scale, shift, nvec, C); }, flush, flush_bytes), rw);
+  }
+  for (int mult : {4, 8, 16, 32}) {
+    const int g = 148 * mult;
+    report("apply grid-stride u4 (today)", g, time_it([&] { apply_gs<<<g, 256>>>(x, y, mean, scale, shift, nvec, C); }, flush, flush_bytes), rw);
+  }
+  {
+    const int g = (int)((nvec + 255) / 256);
+    report("apply grid-stride, 1 vec/thread", g, time_it([&] { apply_gs<<<g, 256>>>(x, y, mean, scale, shift, nvec, C); }, flush, flush_bytes), rw);
+  }
+#define TILE(U, S)                                                                                                              \
+  for (int mult : {0, 4, 8, 16}) {                                                                                              \
+    const int g = mult ? 148 * mult : (int)((nvec + 256 * U - 1) / (256 * U));                                                  \
+    report("apply tile U=" #U " stream=" #S, g, time_it([&] { apply_tile<U, S><<<g, 256>>>(x, y, mean, scale, shift, nvec, C); }, flush, flush_bytes), rw); \
+  }
+  TILE(4, false) TILE(4, true)
+#define TILE32(U)                                                                                                               \
+  for (int mult : {0, 4, 8}) {                                                                                                  \
+    const int64_t nv = nvec / 2;                                                                                                \
+    const int g = mult ? 148 * mult : (int)((nv + 256 * U - 1) / (256 * U));                                                    \
+    report("apply tile32 U=" #U, g, time_it([&] { apply_tile32<U><<<g, 256>>>(x, y, mean, scale, shift, nv, C); }, flush, flush_bytes), rw); \
+  }
+  TILE32(2)
+#define STATS(U, S)                                                                                                             \
+  for (int mult : {4, 8, 16, 64}) {                                                                                             \
+    const int g = 148 * mult;                                                                                                   \
+    report("stats tile U=" #U " stream=" #S, g, time_it([&] { stats_tile<U, S><<<g, 256>>>(x, nvec, C, partials); }, flush, flush_bytes), ro); \
+  }
+  STATS(4, false) STATS(8, true)
+  for (int mult : {4, 8, 16, 32}) {
+    const int g = 148 * mult;
+    report("pure read (xor)", g, time_it([&] { read_flush<<<g, 256>>>((const uint4*)x, nvec, g_sink); }, flush, flush_bytes), ro);
+  }
+  // context: plain device-to-device copy of the same tensor
+  report("cudaMemcpyAsync D2D", 0, time_it([&] { cudaMemcpyAsync(y, x, elems * 2, cudaMemcpyDeviceToDevice); }, flush, flush_bytes), rw);
+  CK(cudaDeviceSynchronize());
+  CK(cudaGetLastError());
+  return 0;
+}
