@@ -31,3 +31,9 @@ t(lambda: F.confusion_counts(lg, tg), lg.numel() * 4 + tg.numel() * 8, "confusio
 lg.requires_grad_(True)
 from multimodal_segmentation_project_b200.utils import metrics as M
 t(lambda: M.combined_loss(lg, tg), lg.numel() * 4 + tg.numel() * 8, "seg_loss fwd(+finalize)")
+# the tiny per-channel kernels (latency-bound): partial sums -> per-channel vectors
+gam = torch.ones(C, device=dev); bet = torch.zeros(C, device=dev); rm_ = torch.zeros(C, device=dev); rv_ = torch.ones(C, device=dev)
+nbt = torch.zeros(1, dtype=torch.int64, device=dev)
+t(lambda: check(L.b200_bn_finalize(1, _ptr(x), _ptr(part), N * S, C, _ptr(gam), _ptr(bet), 1e-5, 0.1, 1, _ptr(rm_), _ptr(rv_), _ptr(nbt),
+                                   _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]), _ptr(stats[3]), _stream())), 592 * 2 * C * 4, "bn_finalize")
+t(lambda: check(L.b200_bn_bwd_finalize(_ptr(part), N * S, C, _ptr(gam), _ptr(bet), _ptr(sums), _stream())), 296 * 2 * C * 4, "bn_bwd_finalize")

@@ -1,0 +1,36 @@
+"""Per-kernel device time of the eager train step (2x128^3 bf16) from torch.profiler (CUPTI activity records:
+warm caches, real back-to-back execution — unlike the ncu launch list, which replays every kernel cold and serialised)."""
+import sys, os, collections
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from torch.profiler import profile, ProfilerActivity
+from multimodal_segmentation_project_b200 import functional as F
+from multimodal_segmentation_project_b200.dp import DataParallelTrainer
+from multimodal_segmentation_project_b200.models.unet import UNet3D
+from multimodal_segmentation_project_b200.synthetic import structured_volume
+from multimodal_segmentation_project_b200.utils import metrics as M
+
+dev = torch.device("cuda")
+torch.manual_seed(0)
+model = UNet3D(1, 4, dropout_rate=0.0).to(dev).train()
+tr = DataParallelTrainer(model, M.combined_loss, lr=1e-3, autocast_dtype=torch.bfloat16, metrics_fn=lambda lg, y: F.confusion_counts(lg, y))
+x, y = structured_volume(2, 128, seed=1234)
+x, y = x.to(dev), y.to(dev)
+for _ in range(3):
+    tr.step(x, y)
+torch.cuda.synchronize()
+steps = 3
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(steps):
+        tr.step(x, y)
+    torch.cuda.synchronize()
+agg = collections.defaultdict(lambda: [0, 0.0])
+t0, t1 = None, None
+for e in prof.events():
+    if e.device_type == torch.autograd.DeviceType.CUDA:
+        agg[e.name][0] += 1
+        agg[e.name][1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
+tot = sum(v for _, v in agg.values())
+print(f"{sum(c for c, _ in agg.values()) // steps} launches/step, sum of kernel time {tot / steps / 1e3:.3f} ms/step")
+for n, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+    print(f"{v / steps / 1e3:8.3f} ms {100 * v / tot:5.1f}% x{c // steps:3d}  avg {v / c:7.1f} us  {n[:100]}")

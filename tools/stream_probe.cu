@@ -207,6 +207,19 @@ int b200_bn_act_bwd_apply(int dtype, const void* gy, const void* x, void* dx, co
 static bool g_read_flush = false;
 static uint32_t* g_sink = nullptr;
 
+// read-only pass in ascending or descending address order (block-contiguous chunks, so that "descending" really
+// starts at the end of the tensor)
+template <bool REV>
+__global__ void __launch_bounds__(256) read_dir(const uint4* __restrict__ p, int64_t n, uint32_t* out) {
+  const int64_t per_block = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t blk = REV ? (int64_t)gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const int64_t lo = blk * per_block, hi = min(n, lo + per_block);
+  uint32_t a = 0;
+  if (!REV) for (int64_t i = lo + threadIdx.x; i < hi; i += 256) { uint4 v = p[i]; a ^= v.x ^ v.y ^ v.z ^ v.w; }
+  else for (int64_t i = hi - 1 - threadIdx.x; i >= lo; i -= 256) { uint4 v = p[i]; a ^= v.x ^ v.y ^ v.z ^ v.w; }
+  if (a == 0x12345678u) *out = a;
+}
+
 template <typename F>
 static float time_it(F&& launch, void* flush, size_t flush_bytes, int iters = 7) {
   cudaEvent_t a, b;
@@ -282,6 +295,23 @@ int main(int argc, char** argv) {
   for (int mult : {4, 8, 16, 32}) {
     const int g = 148 * mult;
     report("pure read (xor)", g, time_it([&] { read_flush<<<g, 256>>>((const uint4*)x, nvec, g_sink); }, flush, flush_bytes), ro);
+  }
+  // producer -> consumer through L2: y is written ascending by the apply kernel, then read ascending / descending
+  {
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int rev = 0; rev < 2; ++rev) {
+      std::vector<float> ts;
+      for (int it = 0; it < 7; ++it) {
+        read_flush<<<148 * 8, 256>>>((const uint4*)flush, (int64_t)(flush_bytes / 16), g_sink);
+        apply_hoist<4><<<1184, 256>>>(x, y, mean, scale, shift, nvec, C);
+        cudaEventRecord(a);
+        if (rev) read_dir<true><<<1184, 256>>>((const uint4*)y, nvec, g_sink); else read_dir<false><<<1184, 256>>>((const uint4*)y, nvec, g_sink);
+        cudaEventRecord(b); cudaEventSynchronize(b);
+        float ms; cudaEventElapsedTime(&ms, a, b); ts.push_back(ms);
+      }
+      std::sort(ts.begin(), ts.end());
+      report(rev ? "read y DESC after writer ASC" : "read y ASC after writer ASC", 1184, ts[3], ro);
+    }
   }
   // context: plain device-to-device copy of the same tensor
   report("cudaMemcpyAsync D2D", 0, time_it([&] { cudaMemcpyAsync(y, x, elems * 2, cudaMemcpyDeviceToDevice); }, flush, flush_bytes), rw);
