@@ -145,6 +145,7 @@ def test_confusion_ragged_sizes(cuda_dev):
 CONV_CASES = [
     # N, D, H, W, c0, c1, Cout
     (2, 6, 5, 7, 1, 0, 16),
+    (1, 9, 17, 41, 1, 0, 16),  # stem: several w / h / d tiles with ragged edges
     (1, 8, 8, 8, 16, 0, 16),
     (2, 4, 6, 10, 16, 0, 32),
     (1, 5, 4, 6, 32, 32, 32),
