@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "tma_maps.cuh"
+#include "partial_reduce.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -213,29 +214,19 @@ wgrad_tc_kernel(const WgParams g, const __grid_constant__ CUtensorMap tm_p, cons
   if (warp == 4) tc::tmem_dealloc(tmem_base, 512);
 }
 
-// partial[(qslab, mchunk, spatial cta)][m 64][tap 27][n 16] -> dw[co][ci][27]
-__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int spatial, int mchunks, int mrows, int Cout, int Cin,
-                                       int swapped, float* __restrict__ dw, int lanes_per_out) {
-  const int64_t stride = (int64_t)mrows * 27 * 16;
-  const int64_t total = (int64_t)Cout * Cin * 27;
-  // lanes_per_out = 32: one warp per output (many partials); 1: one thread per output (few partials, many outputs)
-  const int lane = lanes_per_out == 32 ? (threadIdx.x & 31) : 0;
-  const int shift = lanes_per_out == 32 ? 5 : 0;
-  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> shift; i < total; i += ((int64_t)gridDim.x * blockDim.x) >> shift) {
-    const int tap = (int)(i % 27);
-    const int ci = (int)((i / 27) % Cin);
-    const int co = (int)(i / (27 * (int64_t)Cin));
+// partial[(qslab, mchunk)][spatial cta][m 64][tap 27][n 16] -> dw[co][ci][27]
+struct WgMap {
+  int mchunks, Cout, Cin, swapped;
+  __device__ int64_t operator()(int group, int64_t e) const {
+    const int qslab = group / mchunks, mchunk = group % mchunks;
+    const int nl = (int)(e % 16), t = (int)((e / 16) % 27), mm = (int)(e / (16 * 27));
+    const int m = mchunk * 64 + mm, nn = qslab * 16 + nl;
     // M side = dY (co) and N side = X (ci) unless swapped; swapped results carry the mirrored tap
-    const int m = swapped ? ci : co, nn = swapped ? co : ci;
-    const int t = swapped ? 26 - tap : tap;
-    const int mchunk = m / 64, mm = m % 64, qslab = nn / 16, nl = nn % 16;
-    const float* src = partial + (((int64_t)qslab * mchunks + mchunk) * spatial) * stride + ((int64_t)mm * 27 + t) * 16 + nl;
-    double s = 0.0;
-    for (int c = lane; c < spatial; c += lanes_per_out) s += (double)src[(int64_t)c * stride];
-    if (lanes_per_out == 32) s = warp_sum_d(s);
-    if (lane == 0) dw[i] = (float)s;
+    const int co = swapped ? nn : m, ci = swapped ? m : nn, tap = swapped ? 26 - t : t;
+    if (co >= Cout || ci >= Cin) return -1;
+    return ((int64_t)co * Cin + ci) * 27 + tap;
   }
-}
+};
 
 struct WgPlan { int swapped, cp, cq, mslabs, mchunks, qslabs, dseg, dblocks, tiles_w, tiles_h, spatial; size_t smem; };
 
@@ -422,26 +413,17 @@ convt_wgrad_tc_kernel(const CtParams g, const __grid_constant__ CUtensorMap tm_x
   if (warp == 4) tc::tmem_dealloc(tmem_base, 128);
 }
 
-// partial[(qslab, mchunk, spatial)][m][child*16 + col] -> dw[ci][co][child]
-__global__ void convt_wgrad_tc_reduce_kernel(const float* __restrict__ partial, int spatial, int mchunks, int mrows, int Cin, int Cout,
-                                             float* __restrict__ dw, int lanes_per_out) {
-  const int64_t total = (int64_t)Cin * Cout * 8;
-  const int64_t stride = (int64_t)mrows * 128;
-  // lanes_per_out = 32: one warp per output (many partials); 1: one thread per output (few partials, many outputs)
-  const int lane = lanes_per_out == 32 ? (threadIdx.x & 31) : 0;
-  const int shift = lanes_per_out == 32 ? 5 : 0;
-  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> shift; i < total; i += ((int64_t)gridDim.x * blockDim.x) >> shift) {
-    const int child = (int)(i % 8);
-    const int co = (int)((i / 8) % Cout);
-    const int ci = (int)(i / (8 * (int64_t)Cout));
-    const int mchunk = ci / 64, mm = ci % 64, qslab = co / 16, cl = co % 16;
-    const float* src = partial + (((int64_t)qslab * mchunks + mchunk) * spatial) * stride + (int64_t)mm * 128 + child * 16 + cl;
-    double s = 0.0;
-    for (int c = lane; c < spatial; c += lanes_per_out) s += (double)src[(int64_t)c * stride];
-    if (lanes_per_out == 32) s = warp_sum_d(s);
-    if (lane == 0) dw[i] = (float)s;
+// partial[(qslab, mchunk)][spatial][m][child*16 + col] -> dw[ci][co][child]
+struct CtMap {
+  int mchunks, Cin, Cout;
+  __device__ int64_t operator()(int group, int64_t e) const {
+    const int qslab = group / mchunks, mchunk = group % mchunks;
+    const int cl = (int)(e % 16), child = (int)((e / 16) % 8), mm = (int)(e / 128);
+    const int ci = mchunk * 64 + mm, co = qslab * 16 + cl;
+    if (ci >= Cin || co >= Cout) return -1;
+    return ((int64_t)ci * Cout + co) * 8 + child;
   }
-}
+};
 
 struct CtPlan { int mslabs, mchunks, qslabs, mrows, dseg, dblocks, tiles_w, tiles_h, spatial; size_t smem; };
 CtPlan make_ct_plan(int Cin, int Cout, int N, int D, int H, int W) {
@@ -493,10 +475,7 @@ int b200_convt2_wgrad_tc(const void* x, const void* gy, float* dw, void* workspa
   dim3 grid((unsigned)pl.spatial, (unsigned)pl.mchunks, (unsigned)pl.qslabs);
   convt_wgrad_tc_kernel<<<grid, kCtThreads, pl.smem, stream>>>(g, tm_x);
   B200_CHECK_LAUNCH("convt2_wgrad_tc");
-  const int64_t total = (int64_t)Cin * Cout * 8;
-  const int lpo = pl.spatial >= 64 ? 32 : 1;
-  convt_wgrad_tc_reduce_kernel<<<b200_grid_for(total * lpo, 256, B200_NUM_SMS * 16), 256, 0, stream>>>((const float*)workspace, pl.spatial, pl.mchunks,
-                                                                                                     pl.mrows, Cin, Cout, dw, lpo);
+  launch_partial_reduce((const float*)workspace, pl.spatial, (int64_t)pl.mrows * 128, pl.qslabs * pl.mchunks, CtMap{pl.mchunks, Cin, Cout}, dw, stream);
   B200_CHECK_LAUNCH("convt2_wgrad_tc_reduce");
   return B200_OK;
 }
@@ -551,10 +530,8 @@ int b200_conv3d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const v
   dim3 grid((unsigned)pl.spatial, (unsigned)pl.mchunks, (unsigned)pl.qslabs);
   wgrad_tc_kernel<<<grid, kThreads, pl.smem, stream>>>(g, tm_p, tm_q0, tm_q1);
   B200_CHECK_LAUNCH("conv3d_wgrad_tc");
-  const int64_t total = (int64_t)Cout * (c0 + c1) * 27;
-  const int lpo = pl.spatial >= 64 ? 32 : 1;
-  wgrad_tc_reduce_kernel<<<b200_grid_for(total * lpo, 256, B200_NUM_SMS * 16), 256, 0, stream>>>((const float*)workspace, pl.spatial, pl.mchunks, g.mrows,
-                                                                                         Cout, c0 + c1, pl.swapped, dw, lpo);
+  launch_partial_reduce((const float*)workspace, pl.spatial, (int64_t)g.mrows * 27 * 16, pl.qslabs * pl.mchunks,
+                        WgMap{pl.mchunks, Cout, c0 + c1, pl.swapped}, dw, stream);
   B200_CHECK_LAUNCH("conv3d_wgrad_tc_reduce");
   return B200_OK;
 }

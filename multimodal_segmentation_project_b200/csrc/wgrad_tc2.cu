@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "tma_maps.cuh"
+#include "partial_reduce.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -219,27 +220,17 @@ wgrad_tc2_kernel(const Wg2Params g, const __grid_constant__ CUtensorMap tm_p, co
   if (warp == 2) tc::tmem_dealloc(tmem_base, g.tmem_cols);
 }
 
-// partial[(qslab, pgroup, spatial)][ps][ci 16][tap 27][co 16] -> dw[co][ci][27]
-__global__ void wgrad_tc2_reduce_kernel(const float* __restrict__ partial, int spatial, int pgroups, int pslabs, int Cout, int Cin,
-                                        float* __restrict__ dw, int lanes_per_out) {
-  const int64_t total = (int64_t)Cout * Cin * 27;
-  const int64_t stride = (int64_t)pslabs * 16 * 27 * 16;
-  // lanes_per_out = 32: one warp per output (many partials); 1: one thread per output (few partials, many outputs)
-  const int lane = lanes_per_out == 32 ? (threadIdx.x & 31) : 0;
-  const int shift = lanes_per_out == 32 ? 5 : 0;
-  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> shift; i < total; i += ((int64_t)gridDim.x * blockDim.x) >> shift) {
-    const int tap = (int)(i % 27);
-    const int ci = (int)((i / 27) % Cin);
-    const int co = (int)(i / (27 * (int64_t)Cin));
-    const int qslab = ci / 16, cl = ci % 16, pslab = co / 16, col = co % 16;
-    const int pgroup = pslab / pslabs, ps = pslab % pslabs;
-    const float* src = partial + (((int64_t)qslab * pgroups + pgroup) * spatial) * stride + (((int64_t)ps * 16 + cl) * 27 + tap) * 16 + col;
-    double s = 0.0;
-    for (int c = lane; c < spatial; c += lanes_per_out) s += (double)src[(int64_t)c * stride];
-    if (lanes_per_out == 32) s = warp_sum_d(s);
-    if (lane == 0) dw[i] = (float)s;
+// partial[(qslab, pgroup)][spatial][ps][ci 16][tap 27][co 16] -> dw[co][ci][27]
+struct Wg2Map {
+  int pgroups, pslabs, Cout, Cin;
+  __device__ int64_t operator()(int group, int64_t e) const {
+    const int qslab = group / pgroups, pgroup = group % pgroups;
+    const int col = (int)(e % 16), tap = (int)((e / 16) % 27), cl = (int)((e / (16 * 27)) % 16), ps = (int)(e / (16 * 27 * 16));
+    const int co = (pgroup * pslabs + ps) * 16 + col, ci = qslab * 16 + cl;
+    if (co >= Cout || ci >= Cin) return -1;
+    return ((int64_t)co * Cin + ci) * 27 + tap;
   }
-}
+};
 
 struct Wg2Plan { int pslabs, pgroups, qslabs, dseg, dblocks, tiles_w, tiles_h, spatial, tmem_cols; size_t smem; };
 
@@ -300,10 +291,8 @@ int b200_conv3d_wgrad_tc2(const void* x0, int c0, const void* x1, int c1, const 
   dim3 grid((unsigned)pl.spatial, (unsigned)pl.pgroups, (unsigned)pl.qslabs);
   wgrad_tc2_kernel<<<grid, kThreads, pl.smem, stream>>>(g, tm_p, tm_q0, tm_q1);
   B200_CHECK_LAUNCH("conv3d_wgrad_tc2");
-  const int64_t total = (int64_t)Cout * (c0 + c1) * 27;
-  const int lpo = pl.spatial >= 64 ? 32 : 1;
-  wgrad_tc2_reduce_kernel<<<b200_grid_for(total * lpo, 256, B200_NUM_SMS * 16), 256, 0, stream>>>((const float*)workspace, pl.spatial, pl.pgroups,
-                                                                                                pl.pslabs, Cout, c0 + c1, dw, lpo);
+  launch_partial_reduce((const float*)workspace, pl.spatial, (int64_t)pl.pslabs * 16 * 27 * 16, pl.qslabs * pl.pgroups,
+                        Wg2Map{pl.pgroups, pl.pslabs, Cout, c0 + c1}, dw, stream);
   B200_CHECK_LAUNCH("conv3d_wgrad_tc2_reduce");
   return B200_OK;
 }
