@@ -21,7 +21,8 @@ import sys
 import threading
 import time
 
-os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+# rank 0 prints exactly one JSON line on stdout: NCCL's banner / debug output (whatever NCCL_DEBUG the box exports) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import torch
 

@@ -536,6 +536,11 @@ static int wg_version() {
   if (v < 0) { const char* e = getenv("B200_WGRAD_TC_VERSION"); v = e ? atoi(e) : 2; }
   return v;
 }
+static bool wg_wide_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200_WGRAD_WIDE"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
 // ConvTranspose3d forward / data gradient on the tensor cores (convt_tc.cu)
 bool b200_convt2_tc_supported(int Cin, int Cout);
 int b200_convt2_fwd_tc(const void* x, const float* w, const float* bias, void* y, int N, int D, int H, int W, int Cin, int Cout, cudaStream_t st);
@@ -548,6 +553,11 @@ static int convt_tc_enabled() {
 bool b200_convt2_wgrad_tc_supported(int Cin, int Cout, int N, int D, int H, int W);
 int64_t b200_convt2_wgrad_tc_workspace(int Cin, int Cout, int N, int D, int H, int W);
 int b200_convt2_wgrad_tc(const void* x, const void* gy, float* dw, void* workspace, int N, int D, int H, int W, int Cin, int Cout, cudaStream_t stream);
+// wide-row variant (wgrad_tc3.cu): 32-channel operand rows for layers with >= 32 channels on both sides
+bool b200_conv3d_wgrad_tc3_supported(int c0, int c1, int Cout, int N, int D, int H, int W);
+int64_t b200_conv3d_wgrad_tc3_workspace(int c0, int c1, int Cout, int N, int D, int H, int W);
+int b200_conv3d_wgrad_tc3(const void* x0, int c0, const void* x1, int c1, const void* dy, int Cout, float* dw, void* workspace,
+                          int N, int D, int H, int W, cudaStream_t stream);
 static int g_wgrad_impl = 0;  // 0 auto, 1 CUDA-core, 2 tcgen05
 // in_channels == 1 first layer (conv_stem.cu)
 bool b200_conv_stem_supported(int c0, int c1, int cout);
@@ -659,6 +669,10 @@ extern "C" int64_t b200_conv3d_wgrad_workspace(int c0, int c1, int Cout, int N, 
     const int64_t t = b200_conv3d_wgrad_tc2_workspace(c0, c1, Cout, N, D, H, W);
     if (t > main_bytes) main_bytes = t;
   }
+  if (b200_conv3d_wgrad_tc3_supported(c0, c1, Cout, N, D, H, W)) {
+    const int64_t t = b200_conv3d_wgrad_tc3_workspace(c0, c1, Cout, N, D, H, W);
+    if (t > main_bytes) main_bytes = t;
+  }
   if (b200_conv_stem_wgrad_supported(c0, c1, Cout) && b200_conv_stem_wgrad_workspace(Cout) > main_bytes)
     main_bytes = b200_conv_stem_wgrad_workspace(Cout);
   return b200_bn_partials_bytes(((Cout + 7) / 8) * 8) + main_bytes;
@@ -677,6 +691,7 @@ extern "C" int b200_conv3d_wgrad(int dtype, const void* x0, int c0, const void* 
   float* bpart = (float*)workspace;
   float* partial = (float*)((uint8_t*)workspace + b200_bn_partials_bytes(((Cout + 7) / 8) * 8));
   // v2 (kw on M, kh on N) wins while the channel counts are small; for wide layers v1 fills its 64 M rows with real channels
+  const bool use_v3 = dtype == B200_BF16 && wg_version() >= 2 && wg_wide_enabled() && b200_conv3d_wgrad_tc3_supported(c0, c1, Cout, N, D, H, W);
   const bool use_v2 = wg_version() == 2 && (int64_t)(c0 + c1) * Cout <= 4096 && b200_conv3d_wgrad_tc2_supported(c0, c1, Cout, N, D, H, W);
   const bool tc_ok = dtype == B200_BF16 && (use_v2 ? b200_conv3d_wgrad_tc2_supported(c0, c1, Cout, N, D, H, W)
                                                    : b200_conv3d_wgrad_tc_supported(c0, c1, Cout, N, D, H, W));
@@ -685,6 +700,8 @@ extern "C" int b200_conv3d_wgrad(int dtype, const void* x0, int c0, const void* 
   if (b200_conv_stem_wgrad_supported(c0, c1, Cout) && (dtype == B200_F32 || dtype == B200_BF16)) {
     rc = b200_conv_stem_wgrad(dtype, x0, dy, Cout, dw, partial, N, D, H, W, st);
     if (rc) return rc;
+  } else if (use_v3 && g_wgrad_impl != 1) {
+    rc = b200_conv3d_wgrad_tc3(x0, c0, x1, c1, dy, Cout, dw, partial, N, D, H, W, st);
   } else if (tc_ok && g_wgrad_impl != 1) {
     rc = use_v2 ? b200_conv3d_wgrad_tc2(x0, c0, x1, c1, dy, Cout, dw, partial, N, D, H, W, st)
                 : b200_conv3d_wgrad_tc(x0, c0, x1, c1, dy, Cout, dw, partial, N, D, H, W, st);

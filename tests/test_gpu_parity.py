@@ -629,6 +629,9 @@ WG_CASES = [
     (1, 3, 8, 8, 128, 0, 256),
     (1, 3, 8, 8, 256, 0, 128),
     (1, 19, 33, 18, 16, 0, 16),
+    (2, 9, 20, 33, 32, 0, 32),      # wide-row kernel (32-channel rows): ragged tiles, several d-blocks
+    (1, 5, 16, 16, 64, 0, 64),      # wide rows, 2 x 2 slab pairs
+    (1, 4, 16, 12, 32, 32, 64),     # wide rows, concat input
 ]
 
 
