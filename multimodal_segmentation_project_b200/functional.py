@@ -11,6 +11,8 @@ from __future__ import annotations
 
 import ctypes
 
+import os
+
 import torch
 
 from . import _lib
@@ -134,21 +136,49 @@ def conv3d_k3_raw(x0, x1, wpack, bias, co0, co1=0, impl=1):
     return y0, y1
 
 
-def conv3d_wgrad_raw(x0, x1, dy, want_bias=True):
+def conv3d_wgrad_raw(x0, x1, dy, want_bias=True, side=None):
+    """side: a stream already ordered after the producers of x / dy (see fork_side); the launch then goes there and the
+    call returns (dw, db, workspace) — the caller keeps `workspace` alive until it has joined the side stream."""
     L = _lib.load()
     N, D, H, W, c0 = x0.shape
     c1 = 0 if x1 is None else x1.shape[-1]
     Cout = dy.shape[-1]
     ws_bytes = L.b200_conv3d_wgrad_workspace(c0, c1, Cout, N, D, H, W)
+    # all buffers come from the CURRENT stream's pool, whichever stream the kernels run on
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x0.device)
     dw = torch.empty((Cout, c0 + c1, 3, 3, 3), dtype=torch.float32, device=x0.device)
     db = torch.empty(Cout, dtype=torch.float32, device=x0.device) if want_bias else None
     check(
         L.b200_conv3d_wgrad(_dt(x0), _ptr(x0), c0, _ptr(x1), c1, _ptr(dy), Cout, _ptr(dw), _ptr(db), _ptr(ws), ws_bytes,
-                            N, D, H, W, _stream()),
+                            N, D, H, W, _stream() if side is None else side.cuda_stream),
         "conv3d_wgrad",
     )
-    return dw, db
+    return (dw, db) if side is None else (dw, db, ws)
+
+
+# The weight gradient and the data gradient of a layer read the same dY and are independent: the weight gradient runs on
+# a side stream (fork after dY is produced, join before backward() returns).  The deep layers (16^3, 8^3 voxels) launch
+# fewer CTAs than the GPU has SMs, so the two kernels genuinely run side by side; under CUDA-graph capture the fork/join
+# becomes two parallel branches of the graph.
+_side_streams = {}
+_overlap_wgrad = os.environ.get("B200_OVERLAP_WGRAD", "1") != "0"
+
+
+def fork_side(device):
+    """Returns a side stream that waits for everything enqueued so far on the current stream (None if disabled)."""
+    if not _overlap_wgrad:
+        return None
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    side = _side_streams.get(key)
+    if side is None:
+        side = _side_streams[key] = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    return side
+
+
+def join_side(side, device):
+    if side is not None:
+        torch.cuda.current_stream(device).wait_stream(side)
 
 
 def set_wgrad_impl(impl: int) -> None:
@@ -237,19 +267,28 @@ class _ConvBNAct(torch.autograd.Function):
             "bn_act_bwd_apply",
         )
         dw = db = None
-        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+        need_w = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        need_x = ctx.needs_input_grad[0] or (x1 is not None and ctx.needs_input_grad[1])
+        side = keep = None
+        if need_w:
             # A conv bias feeding a batch-statistics BatchNorm has an exactly-zero gradient (the mean subtraction
             # cancels it; the reference computes round-off noise around 0): skip the column-sum pass.
-            dw, db = conv3d_wgrad_raw(x0, x1, dconv, want_bias=not ctx.training)
+            side = fork_side(dev) if need_x else None
+            if side is None:
+                dw, db = conv3d_wgrad_raw(x0, x1, dconv, want_bias=not ctx.training)
+            else:
+                dw, db, keep = conv3d_wgrad_raw(x0, x1, dconv, want_bias=not ctx.training, side=side)
             if db is None:
                 db = torch.zeros(Cout, dtype=torch.float32, device=dev)
         dx0 = dx1 = None
-        if ctx.needs_input_grad[0] or (x1 is not None and ctx.needs_input_grad[1]):
+        if need_x:
             c0 = x0.shape[-1]
             c1 = 0 if x1 is None else x1.shape[-1]
             impl = conv3d_select_impl(dconv, None, c0, c1, ctx.impl_req)
             wpack = pack_conv3_weights(weight, pack_mode(impl, True), conv_out.dtype)
             dx0, dx1 = conv3d_k3_raw(dconv, None, wpack, None, c0, c1, impl)
+        join_side(side, dev)
+        del keep
         return (dx0, dx1, dw, db, dgamma, dbeta, None, None, None, None, None, None, None, None)
 
 
@@ -310,20 +349,24 @@ class _ConvT2(torch.autograd.Function):
         N, D, H, W, Cin = x.shape
         Cout = weight.shape[1]
         w32 = _f32(weight)
-        gx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            gx = torch.empty_like(x)
-            check(L.b200_convt2_bwd_data(_dt(x), _ptr(gy), _ptr(w32), _ptr(gx), N, D, H, W, Cin, Cout, _stream()), "convt2_bwd_data")
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+        gx = dw = db = ws = side = None
+        need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        if need_w:  # on a side stream next to the data gradient (see fork_side)
+            side = fork_side(x.device) if ctx.needs_input_grad[0] else None
             ws_bytes = L.b200_convt2_wgrad_workspace(Cin, Cout, N, D, H, W)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
             dw = torch.empty_like(w32)
             db = torch.empty(Cout, dtype=torch.float32, device=x.device)
             check(
                 L.b200_convt2_bwd_weight(_dt(x), _ptr(x), _ptr(gy), _ptr(dw), _ptr(db), _ptr(ws), ws_bytes, N, D, H, W, Cin, Cout,
-                                         _stream()),
+                                         _stream() if side is None else side.cuda_stream),
                 "convt2_bwd_weight",
             )
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            check(L.b200_convt2_bwd_data(_dt(x), _ptr(gy), _ptr(w32), _ptr(gx), N, D, H, W, Cin, Cout, _stream()), "convt2_bwd_data")
+        join_side(side, x.device)
+        del ws
         return gx, dw, db
 
 
