@@ -19,6 +19,8 @@ from __future__ import annotations
 
 from typing import Callable, Optional
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -109,6 +111,9 @@ class DataParallelTrainer:
             self.opt = FlatAdamW(self.fp.flat, self.fp.grad, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         self.overlap = overlap and self.world > 1 and dev.type == "cuda" and self.fp.early_sentinel is not None
         self._side = torch.cuda.Stream(device=dev) if self.overlap else None
+        # weight gradients run on a side stream and are joined at the end of backward / before a bucket is gathered:
+        # safe here because step() detaches the gradients first (autograd stores, never accumulates)
+        self._defer_wgrad = dev.type == "cuda" and os.environ.get("B200_DEFER_WGRAD_JOIN", "1") != "0"
         self._early_done = False
         if self.overlap:
             self.fp.early_sentinel.register_post_accumulate_grad_hook(self._early_hook)
@@ -123,6 +128,7 @@ class DataParallelTrainer:
     def _early_hook(self, _param):
         # called by autograd right after the sentinel's gradient was accumulated: everything in the
         # early bucket is final -> reduce it on the side stream while the encoder backward continues
+        self._join_wgrads()
         self.fp.gather_grads("early")
         cur = torch.cuda.current_stream()
         self._side.wait_stream(cur)
@@ -130,7 +136,13 @@ class DataParallelTrainer:
             dist.all_reduce(self.fp.buckets()[0], op=dist.ReduceOp.SUM, group=self.pg)
         self._early_done = True
 
+    def _join_wgrads(self):
+        if self._defer_wgrad:
+            from . import functional as F
+            F.join_pending()
+
     def allreduce_grads(self):
+        self._join_wgrads()
         if self.overlap and self._early_done:
             self.fp.gather_grads("late")
         else:
@@ -149,6 +161,16 @@ class DataParallelTrainer:
 
     # -- one training step -------------------------------------------------------------------------
     def _step_impl(self, x, y):
+        if self._defer_wgrad:
+            from . import functional as F
+            F.set_deferred_wgrad_join(True)
+        try:
+            return self._step_body(x, y)
+        finally:
+            if self._defer_wgrad:
+                F.set_deferred_wgrad_join(False)
+
+    def _step_body(self, x, y):
         self.fp.detach_grads()
         if self.autocast_dtype is not None and x.is_cuda:
             with torch.autocast("cuda", dtype=self.autocast_dtype):

@@ -176,9 +176,39 @@ def fork_side(device):
     return side
 
 
-def join_side(side, device):
-    if side is not None:
+def join_side(side, device, *keep):
+    """Joins the side stream now — or, in deferred mode, at the end of the running backward pass (the weight gradients
+    then also overlap the following layers' HBM-bound BatchNorm kernels); `keep` = tensors the side-stream kernels still
+    read or write, held until the join so that their memory is not handed out again on the main stream."""
+    if side is None:
+        return
+    if not _defer_join:
         torch.cuda.current_stream(device).wait_stream(side)
+        return
+    _pending.append((side, device, keep))
+    torch.autograd.Variable._execution_engine.queue_callback(join_pending)
+
+
+# Deferred mode is only safe when nothing consumes a parameter gradient on the main stream before the end of backward
+# (p.grad is None, so autograd's AccumulateGrad just stores the tensor): DataParallelTrainer's detached-gradient mode.
+_defer_join = False
+_pending = []
+
+
+def set_deferred_wgrad_join(on: bool) -> None:
+    global _defer_join
+    join_pending()
+    _defer_join = bool(on)
+
+
+def join_pending() -> None:
+    """Orders the current stream after every outstanding side-stream weight gradient and releases the held tensors."""
+    seen = set()
+    for side, device, _ in _pending:
+        if id(side) not in seen:
+            seen.add(id(side))
+            torch.cuda.current_stream(device).wait_stream(side)
+    _pending.clear()
 
 
 def set_wgrad_impl(impl: int) -> None:
@@ -287,7 +317,7 @@ class _ConvBNAct(torch.autograd.Function):
             impl = conv3d_select_impl(dconv, None, c0, c1, ctx.impl_req)
             wpack = pack_conv3_weights(weight, pack_mode(impl, True), conv_out.dtype)
             dx0, dx1 = conv3d_k3_raw(dconv, None, wpack, None, c0, c1, impl)
-        join_side(side, dev)
+        join_side(side, dev, x0, x1, dconv, keep)
         del keep
         return (dx0, dx1, dw, db, dgamma, dbeta, None, None, None, None, None, None, None, None)
 
@@ -365,7 +395,7 @@ class _ConvT2(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
             check(L.b200_convt2_bwd_data(_dt(x), _ptr(gy), _ptr(w32), _ptr(gx), N, D, H, W, Cin, Cout, _stream()), "convt2_bwd_data")
-        join_side(side, x.device)
+        join_side(side, x.device, x, gy, ws)
         del ws
         return gx, dw, db
 
