@@ -13,3 +13,10 @@ for _ in range(3):
     F.conv3d_k3_raw(x0, x1, wp, b, 16, 0, impl=2)
     F.conv3d_wgrad_raw(x0, x1, dy, want_bias=False)
 torch.cuda.synchronize(); print("ok")
+# wide-row weight gradient (wgrad_tc3_kernel): decoder.2.c0's shape, 2x64^3, (32+32) -> 32
+S2 = 64
+q0 = torch.randn(N, S2, S2, S2, 32, device=dev).bfloat16(); q1 = torch.randn(N, S2, S2, S2, 32, device=dev).bfloat16()
+dy2 = torch.randn(N, S2, S2, S2, 32, device=dev).bfloat16()
+for _ in range(3):
+    F.conv3d_wgrad_raw(q0, q1, dy2, want_bias=False)
+torch.cuda.synchronize(); print("ok wide")
