@@ -409,7 +409,11 @@ int b200_conv3d_k3_tc2(const void* x0, int c0, const void* x1, int c1, const voi
   static int splitk_enabled = -1;
   if (splitk_enabled < 0) { const char* e = getenv("B200_CONV_SPLITK"); splitk_enabled = e ? atoi(e) : 1; }
   if (splitk_enabled && ctas * 2 <= B200_NUM_SMS && p.slabs >= 4) {
-    int want = (int)((2 * B200_NUM_SMS + ctas - 1) / ctas);
+    // aim for ONE wave of resident CTAs: a second wave repeats the fixed per-CTA cost (TMEM allocation, first weight slab,
+    // fp32 partial drain), which dominates these small problems
+    const int per_sm = 2 * smem <= (size_t)220 * 1024 ? 2 : 1;
+    int want = (int)((per_sm * B200_NUM_SMS) / ctas);
+    if (want < 1) want = 1;
     if (want > p.slabs) want = p.slabs;
     p.slabs_per = (p.slabs + want - 1) / want;
     p.ksplit = (p.slabs + p.slabs_per - 1) / p.slabs_per;

@@ -34,3 +34,11 @@ tot = sum(v for _, v in agg.values())
 print(f"{sum(c for c, _ in agg.values()) // steps} launches/step, sum of kernel time {tot / steps / 1e3:.3f} ms/step")
 for n, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
     print(f"{v / steps / 1e3:8.3f} ms {100 * v / tot:5.1f}% x{c // steps:3d}  avg {v / c:7.1f} us  {n[:100]}")
+# per-launch durations of the convolution kernels of the LAST profiled step, in launch order
+# (forward: enc0.c1 .. bott .. dec3.c1, then the data gradients in reverse order)
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and ("conv3d_tc" in e.name or "splitk" in e.name)]
+evs.sort(key=lambda e: e.time_range.start)
+per = len(evs) // steps
+last = evs[-per:]
+print("conv launches of one step (us):")
+print(" ".join(f"{'T3' if 'tc3' in e.name else ('sk' if 'splitk' in e.name else 'T2')}:{(e.device_time if hasattr(e, 'device_time') else e.cuda_time):.0f}" for e in last))
