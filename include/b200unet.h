@@ -147,6 +147,10 @@ int b200_channel_sum(int dtype, const void* x, int64_t M, int C, float* partials
 int b200_maxpool2_fwd(int dtype, const void* x, void* y, int N, int D, int H, int W, int C, void* stream);
 /* gradient goes to the first maximum in (d,h,w) scan order, as ATen's max_pool3d_with_indices */
 int b200_maxpool2_bwd(int dtype, const void* x, const void* gy, void* gx, int N, int D, int H, int W, int C, void* stream);
+/* the encoder output feeds both the pool and the decoder's skip connection (models/unet.py:69-71,84): gx = gskip + scatter(gy)
+ * in one pass instead of the pool backward followed by autograd's accumulation kernel */
+int b200_maxpool2_bwd_add(int dtype, const void* x, const void* gy, const void* gskip, void* gx, int N, int D, int H, int W, int C,
+                          void* stream);
 
 /* ---------------------------------------------------------------- ConvTranspose3d(k=2,s=2)  models/unet.py:56-58,79
  * x [N,D,H,W,Cin] -> y [N,2D,2H,2W,Cout]; w is the torch layout [Cin, Cout, 2,2,2] fp32. */

@@ -63,6 +63,7 @@ def _declare(lib) -> None:
         "b200_channel_sum": (I, [I, P, L, I, P, P, P]),
         "b200_maxpool2_fwd": (I, [I, P, P, I, I, I, I, I, P]),
         "b200_maxpool2_bwd": (I, [I, P, P, P, I, I, I, I, I, P]),
+        "b200_maxpool2_bwd_add": (I, [I, P, P, P, P, I, I, I, I, I, P]),
         "b200_convt2_fwd": (I, [I, P, P, P, P, I, I, I, I, I, I, P]),
         "b200_convt2_bwd_data": (I, [I, P, P, P, I, I, I, I, I, I, P]),
         "b200_convt2_wgrad_workspace": (L, [I, I, I, I, I, I]),

@@ -398,7 +398,8 @@ maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int D, in
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy, T* __restrict__ gx, int N, int D, int H, int W, int C) {
+maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy, const T* __restrict__ gskip, T* __restrict__ gx, int N, int D, int H, int W,
+                    int C) {
   const int OD = D / 2, OH = H / 2, OW = W / 2, CV = C / 8;
   const int64_t total = (int64_t)N * OD * OH * OW * CV;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -435,6 +436,14 @@ maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy, T* __rest
       float o[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[k] = (arg[k] == p) ? gf[k] : 0.f;
+      if (gskip) {  // fused gradient accumulation of the skip connection: gx = gskip + scatter(gy), rounded once like torch's add
+        Vec8<T> sv;
+        sv.load(gskip + row * C + cv * 8);
+        float sf[8];
+        sv.get(sf);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += sf[k];
+      }
       Vec8<T> ov;
       ov.set(o);
       ov.store(gx + row * C + cv * 8);
@@ -786,19 +795,29 @@ extern "C" int b200_maxpool2_fwd(int dtype, const void* x, void* y, int N, int D
   return B200_OK;
 }
 
-extern "C" int b200_maxpool2_bwd(int dtype, const void* x, const void* gy, void* gx, int N, int D, int H, int W, int C, void* stream) {
-  int rc = check_rows("maxpool2_bwd", (int64_t)N * D * H * W, C);
+static int maxpool2_bwd_impl(const char* name, int dtype, const void* x, const void* gy, const void* gskip, void* gx, int N, int D, int H, int W,
+                             int C, void* stream) {
+  int rc = check_rows(name, (int64_t)N * D * H * W, C);
   if (rc) return rc;
-  B200_REQUIRE(x && gy && gx && D >= 2 && H >= 2 && W >= 2, B200_ERR_SHAPE, "maxpool2_bwd: spatial dims must be >= 2");
+  B200_REQUIRE(x && gy && gx && D >= 2 && H >= 2 && W >= 2, B200_ERR_SHAPE, "%s: spatial dims must be >= 2", name);
   cudaStream_t st = (cudaStream_t)stream;
-  if ((D | H | W) & 1) {
-    const size_t esz = dtype == B200_F32 ? 4 : 2;
-    B200_CUDA(cudaMemsetAsync(gx, 0, (size_t)N * D * H * W * C * esz, st));
+  if ((D | H | W) & 1) {  // voxels outside every 2x2x2 window: gradient 0 (+ the skip gradient)
+    const size_t bytes = (size_t)N * D * H * W * C * (dtype == B200_F32 ? 4 : 2);
+    if (gskip) B200_CUDA(cudaMemcpyAsync(gx, gskip, bytes, cudaMemcpyDeviceToDevice, st));
+    else B200_CUDA(cudaMemsetAsync(gx, 0, bytes, st));
   }
   const int64_t items = (int64_t)N * (D / 2) * (H / 2) * (W / 2) * (C / 8);
-  B200_DISPATCH_DTYPE(dtype, T, (maxpool2_bwd_kernel<T><<<ew_grid(items), kThreads, 0, st>>>((const T*)x, (const T*)gy, (T*)gx, N, D, H, W, C)));
-  B200_CHECK_LAUNCH("maxpool2_bwd");
+  B200_DISPATCH_DTYPE(dtype, T, (maxpool2_bwd_kernel<T><<<ew_grid(items), kThreads, 0, st>>>((const T*)x, (const T*)gy, (const T*)gskip, (T*)gx, N, D, H, W, C)));
+  B200_CHECK_LAUNCH(name);
   return B200_OK;
+}
+extern "C" int b200_maxpool2_bwd(int dtype, const void* x, const void* gy, void* gx, int N, int D, int H, int W, int C, void* stream) {
+  return maxpool2_bwd_impl("maxpool2_bwd", dtype, x, gy, nullptr, gx, N, D, H, W, C, stream);
+}
+extern "C" int b200_maxpool2_bwd_add(int dtype, const void* x, const void* gy, const void* gskip, void* gx, int N, int D, int H, int W, int C,
+                                     void* stream) {
+  B200_REQUIRE(gskip != nullptr, B200_ERR_SHAPE, "maxpool2_bwd_add: null skip gradient");
+  return maxpool2_bwd_impl("maxpool2_bwd_add", dtype, x, gy, gskip, gx, N, D, H, W, C, stream);
 }
 
 extern "C" int b200_nearest_resize_fwd(int dtype, const void* x, void* y, int N, int D, int H, int W, int OD, int OH, int OW,

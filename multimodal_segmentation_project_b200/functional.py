@@ -356,6 +356,43 @@ def maxpool2(x):
     return _MaxPool2.apply(x)
 
 
+class _SkipPool(torch.autograd.Function):
+    """Encoder hand-off (models/unet.py:69-71): returns (skip, MaxPool3d(2,2)(x)).  Owning both uses of x lets the backward
+    pass add the skip connection's gradient inside the pool-backward kernel instead of in a separate accumulation pass."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x)
+        L = _lib.load()
+        x = x.contiguous()
+        N, D, H, W, C = x.shape
+        y = torch.empty((N, D // 2, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
+        check(L.b200_maxpool2_fwd(_dt(x), _ptr(x), _ptr(y), N, D, H, W, C, _stream()), "maxpool2_fwd")
+        ctx.save_for_backward(x)
+        return x.view_as(x), y
+
+    @staticmethod
+    def backward(ctx, g_skip, g_pool):
+        L = _lib.load()
+        (x,) = ctx.saved_tensors
+        if g_pool is None:
+            return g_skip
+        N, D, H, W, C = x.shape
+        g_pool = g_pool.contiguous()
+        gx = torch.empty_like(x)
+        if g_skip is None:
+            check(L.b200_maxpool2_bwd(_dt(x), _ptr(x), _ptr(g_pool), _ptr(gx), N, D, H, W, C, _stream()), "maxpool2_bwd")
+        else:
+            g_skip = g_skip.contiguous()
+            check(L.b200_maxpool2_bwd_add(_dt(x), _ptr(x), _ptr(g_pool), _ptr(g_skip), _ptr(gx), N, D, H, W, C, _stream()), "maxpool2_bwd_add")
+        return gx
+
+
+def skip_and_pool(x):
+    """(skip, pooled) = (x, maxpool2(x)) with a fused backward."""
+    return _SkipPool.apply(x)
+
+
 # --------------------------------------------------------------------------- ConvTranspose3d(k2,s2)
 class _ConvT2(torch.autograd.Function):
     @staticmethod

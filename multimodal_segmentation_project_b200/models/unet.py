@@ -132,8 +132,8 @@ class UNet3D(nn.Module):
         skips = []
         for down in self.encoder:
             h = down.forward_cl(h, None, impl)
-            skips.append(h)
-            h = F.maxpool2(h)
+            skip, h = F.skip_and_pool(h)  # skip connection + MaxPool3d(2,2); their gradients meet in one kernel
+            skips.append(skip)
         bott = self.bottleneck.forward_cl(h, None, impl)
         h = bott
         skips = skips[::-1]

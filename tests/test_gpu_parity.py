@@ -265,6 +265,18 @@ def test_maxpool_fwd_bwd(cuda_dev, dtype, shape):
     y.backward(cl(gy, dtype))
     assert torch.equal(cf(y), yr.detach())          # max is exact
     assert torch.equal(cf(xc.grad), xr.grad)        # gradient routing to the first maximum: exact
+    # skip + pool with the fused backward: d(skip)/dx + d(pool)/dx, rounded once like torch's accumulation of two grads
+    xs = cl(x, dtype).requires_grad_(True)
+    skip, yp = F.skip_and_pool(xs)
+    gs = torch.randn(x.shape, generator=gen).to(dtype).float()
+    torch.autograd.backward([skip, yp], [cl(gs, dtype), cl(gy, dtype)])
+    want = (gs.to(dtype).float() + xr.grad).to(dtype).float()
+    assert torch.equal(cf(yp), yr.detach()) and torch.equal(cf(skip), x)
+    assert torch.equal(cf(xs.grad), want)
+    xs2 = cl(x, dtype).requires_grad_(True)
+    skip2, yp2 = F.skip_and_pool(xs2)
+    yp2.backward(cl(gy, dtype))                      # only the pool branch used
+    assert torch.equal(cf(xs2.grad), xr.grad)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
