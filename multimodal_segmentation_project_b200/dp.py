@@ -195,7 +195,10 @@ class DataParallelTrainer:
         """Captures the whole step in one CUDA graph (static input buffers)."""
         self.static_x = x_example.clone()
         self.static_y = y_example.clone()
-        s = torch.cuda.Stream()
+        # the step's main chain is captured on a HIGH-priority stream: the side-stream weight gradients (default priority,
+        # needed only at the end of backward) then fill SMs the main chain leaves idle instead of delaying it
+        prio = int(os.environ.get("B200_MAIN_STREAM_PRIORITY", "-1"))
+        s = torch.cuda.Stream(priority=prio)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
@@ -203,7 +206,7 @@ class DataParallelTrainer:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=s):
             self.loss, self.metrics = self._step_impl(self.static_x, self.static_y)
         self.graph = g
         return g
