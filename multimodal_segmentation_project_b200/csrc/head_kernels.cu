@@ -49,6 +49,57 @@ conv1x1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const f
   }
 }
 
+// Fast path for the network's actual head (Cin = 16, Cout <= 4): weights and bias live in registers, two voxels per thread
+// and iteration (their four 16-byte loads are issued before the math), streaming stores of the NCDHW fp32 logits.
+// HBM-bound: 2*Cin B read + 4*Cout B written per voxel (201 MB at 2x128^3).
+template <typename T, int CIN, int COUT>
+__global__ void __launch_bounds__(kThreads)
+conv1x1_fwd_small_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
+                         int64_t N, int64_t S, int round_bf16) {
+  float wr[COUT][CIN], br[COUT];
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) {
+    br[co] = bias ? bias[co] : 0.f;
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) wr[co][ci] = w[co * CIN + ci];
+  }
+  const int64_t total = N * S, stride = (int64_t)gridDim.x * blockDim.x;
+  constexpr int U = 2;
+  for (int64_t v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < total; v0 += U * stride) {
+    Vec8<T> xv[U][CIN / 8];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (v0 + u * stride < total) {
+#pragma unroll
+        for (int c8 = 0; c8 < CIN / 8; ++c8) xv[u][c8].load(x + (v0 + u * stride) * CIN + c8 * 8);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      if (v >= total) continue;
+      float acc[COUT];
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) acc[co] = br[co];
+#pragma unroll
+      for (int c8 = 0; c8 < CIN / 8; ++c8) {
+        float f[8];
+        xv[u][c8].get(f);
+#pragma unroll
+        for (int co = 0; co < COUT; ++co)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[co] = fmaf(f[k], wr[co][c8 * 8 + k], acc[co]);
+      }
+      const int64_t n = v / S, sp = v - n * S;
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) {
+        float o = acc[co];
+        if (round_bf16) o = __bfloat162float(__float2bfloat16_rn(o));
+        __stcs(y + (n * COUT + co) * S + sp, o);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- 1x1x1 backward
 // One pass: gx = gy^T W (rows), and per-block partial dW/db.  P = Cout*(Cin+1) accumulators
 // (the extra column is db).
@@ -313,6 +364,15 @@ extern "C" int b200_conv1x1_fwd(int dtype, const void* x, const float* w, const 
   B200_REQUIRE(x && w && y && N > 0 && S > 0, B200_ERR_SHAPE, "conv1x1_fwd: bad arguments");
   B200_REQUIRE(Cin >= 8 && Cin % 8 == 0 && Cin <= 512, B200_ERR_UNSUPPORTED, "conv1x1_fwd: Cin=%d must be a multiple of 8 in [8,512]", Cin);
   B200_REQUIRE(Cout >= 1 && Cout <= kMaxCo, B200_ERR_UNSUPPORTED, "conv1x1_fwd: Cout=%d outside [1,%d]", Cout, kMaxCo);
+  if (Cin == 16 && Cout >= 2 && Cout <= 4 && (dtype == B200_F32 || dtype == B200_BF16)) {
+    const int g = b200_grid_for(N * S, kThreads * 2, B200_NUM_SMS * 2);  // 94 registers: two resident CTAs per SM, one wave
+#define RUN_FS(T, CO) conv1x1_fwd_small_kernel<T, 16, CO><<<g, kThreads, 0, (cudaStream_t)stream>>>((const T*)x, w, bias, y, N, S, round_bf16)
+    if (dtype == B200_F32) { if (Cout == 4) RUN_FS(float, 4); else if (Cout == 3) RUN_FS(float, 3); else RUN_FS(float, 2); }
+    else { if (Cout == 4) RUN_FS(__nv_bfloat16, 4); else if (Cout == 3) RUN_FS(__nv_bfloat16, 3); else RUN_FS(__nv_bfloat16, 2); }
+#undef RUN_FS
+    B200_CHECK_LAUNCH("conv1x1_fwd_small");
+    return B200_OK;
+  }
   const size_t smem = (size_t)(Cout * Cin + Cout) * sizeof(float);
   const int grid = b200_grid_for(N * S, kThreads, B200_NUM_SMS * 8);
   B200_DISPATCH_DTYPE(dtype, T, (conv1x1_fwd_kernel<T><<<grid, kThreads, smem, (cudaStream_t)stream>>>((const T*)x, w, bias, y, N, S, Cin, Cout, round_bf16)));
@@ -335,7 +395,7 @@ extern "C" int b200_conv1x1_bwd(int dtype, const void* x, const float* w, const 
   B200_REQUIRE(smem <= 200 * 1024, B200_ERR_UNSUPPORTED, "conv1x1_bwd: channel counts too large for shared memory");
   int nblocks = bwd_blocks(N * S);
   if (Cin == 16 && (Cout == 4 || Cout == 2 || Cout == 3)) {
-    nblocks = b200_grid_for(N * S, kThreads, kMaxPartialBlocks);
+    nblocks = b200_grid_for(N * S, kThreads, B200_NUM_SMS * 2);  // 124 registers: two resident CTAs per SM, one wave
 #define RUN_SMALL(T, CO) conv1x1_bwd_small_kernel<T, 16, CO><<<nblocks, kThreads, 0, st>>>((const T*)x, w, gy, (T*)gx, partials, N, S)
     if (dtype == B200_F32) { if (Cout == 4) RUN_SMALL(float, 4); else if (Cout == 3) RUN_SMALL(float, 3); else RUN_SMALL(float, 2); }
     else if (dtype == B200_BF16) { if (Cout == 4) RUN_SMALL(__nv_bfloat16, 4); else if (Cout == 3) RUN_SMALL(__nv_bfloat16, 3); else RUN_SMALL(__nv_bfloat16, 2); }
