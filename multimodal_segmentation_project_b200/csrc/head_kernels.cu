@@ -188,7 +188,7 @@ conv1x1_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const f
 // dW/db tile (Cout*(Cin+1) accumulators) in registers over a grid-stride loop; HBM-bound:
 // 4*Cout B (gy) + 2*Cin B (x) read, 2*Cin B (gx) written per voxel.
 template <typename T, int CIN, int COUT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 conv1x1_bwd_small_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ gy, T* __restrict__ gx,
                          float* __restrict__ partials, int64_t N, int64_t S) {
   __shared__ float ws[COUT * CIN];
@@ -202,42 +202,55 @@ conv1x1_bwd_small_kernel(const T* __restrict__ x, const float* __restrict__ w, c
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) dw[co][ci] = 0.f;
   }
-  const int64_t total = N * S;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t n = v / S, s = v - n * S;
-    float g[COUT];
+  const int64_t total = N * S, stride = (int64_t)gridDim.x * blockDim.x;
+  constexpr int U = 2;  // two voxels per thread in flight: 2 x (COUT gy loads + CIN/8 x loads) issued before the math
+  for (int64_t v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < total; v0 += U * stride) {
+    float g[U][COUT];
+    Vec8<T> xv[U][CIN / 8];
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) g[co] = __ldcs(gy + (n * COUT + co) * S + s);
-    float xf[CIN];
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      if (v < total) {
+        const int64_t n = v / S, sp = v - n * S;
 #pragma unroll
-    for (int c8 = 0; c8 < CIN / 8; ++c8) {
-      Vec8<T> xv;
-      xv.load(x + v * CIN + c8 * 8);
-      float f[8];
-      xv.get(f);
+        for (int co = 0; co < COUT; ++co) g[u][co] = __ldcs(gy + (n * COUT + co) * S + sp);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) xf[c8 * 8 + k] = f[k];
+        for (int c8 = 0; c8 < CIN / 8; ++c8) xv[u][c8].load(x + v * CIN + c8 * 8);
+      }
     }
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) {
-      db[co] += g[co];
-#pragma unroll
-      for (int ci = 0; ci < CIN; ++ci) dw[co][ci] = fmaf(g[co], xf[ci], dw[co][ci]);
-    }
-    if (gx) {
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      if (v >= total) continue;
+      float xf[CIN];
 #pragma unroll
       for (int c8 = 0; c8 < CIN / 8; ++c8) {
-        float o[8];
+        float f[8];
+        xv[u][c8].get(f);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float a = 0.f;
+        for (int k = 0; k < 8; ++k) xf[c8 * 8 + k] = f[k];
+      }
 #pragma unroll
-          for (int co = 0; co < COUT; ++co) a = fmaf(g[co], ws[co * CIN + c8 * 8 + k], a);
-          o[k] = a;
+      for (int co = 0; co < COUT; ++co) {
+        db[co] += g[u][co];
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) dw[co][ci] = fmaf(g[u][co], xf[ci], dw[co][ci]);
+      }
+      if (gx) {
+#pragma unroll
+        for (int c8 = 0; c8 < CIN / 8; ++c8) {
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float a = 0.f;
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) a = fmaf(g[u][co], ws[co * CIN + c8 * 8 + k], a);
+            o[k] = a;
+          }
+          Vec8<T> ov;
+          ov.set(o);
+          ov.store(gx + v * CIN + c8 * 8);
         }
-        Vec8<T> ov;
-        ov.set(o);
-        ov.store(gx + v * CIN + c8 * 8);
       }
     }
   }
