@@ -79,17 +79,21 @@ class FlatParams:
         for _, p in self.order:
             p.grad = None
 
-    def gather_grads(self, which="all"):
+    def gather_grads(self, which="all", accumulate=False):
         lo, hi = {"all": (0, len(self.order)), "early": (0, self.n_early_params), "late": (self.n_early_params, len(self.order))}[which]
         dst, src = [], []
         for (n, p), v in zip(self.order[lo:hi], self._views[lo:hi]):
             if p.grad is None:
-                v.zero_()
+                if not accumulate:
+                    v.zero_()
             else:
                 dst.append(v)
                 src.append(p.grad)
         if dst:
-            torch._foreach_copy_(dst, src)
+            if accumulate:
+                torch._foreach_add_(dst, src)
+            else:
+                torch._foreach_copy_(dst, src)
 
 
 class DataParallelTrainer:
@@ -97,7 +101,7 @@ class DataParallelTrainer:
 
     def __init__(self, model, loss_fn: Callable, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
                  autocast_dtype: Optional[torch.dtype] = torch.bfloat16, process_group=None, overlap=True,
-                 metrics_fn: Optional[Callable] = None, optimizer_factory=None):
+                 metrics_fn: Optional[Callable] = None, optimizer_factory=None, accumulation_steps: int = 1):
         self.model, self.loss_fn, self.metrics_fn = model, loss_fn, metrics_fn
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
@@ -108,7 +112,9 @@ class DataParallelTrainer:
             self.opt = optimizer_factory(self.fp)
         else:
             from .functional import FlatAdamW
-            self.opt = FlatAdamW(self.fp.flat, self.fp.grad, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+            named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]  # model.parameters() order = torch.optim's
+            self.opt = FlatAdamW(self.fp.flat, self.fp.grad, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                                 named_params=named, offsets=self.fp.offsets)
         self.overlap = overlap and self.world > 1 and dev.type == "cuda" and self.fp.early_sentinel is not None
         self._side = torch.cuda.Stream(device=dev) if self.overlap else None
         # weight gradients run on a side stream and are joined at the end of backward / before a bucket is gathered:
@@ -117,6 +123,10 @@ class DataParallelTrainer:
         self._early_done = False
         if self.overlap:
             self.fp.early_sentinel.register_post_accumulate_grad_hook(self._early_hook)
+        # gradient accumulation (accelerator.accumulate, train_unet.py:221): micro-steps 1..k-1 only add their gradients
+        # (of loss / k) into the flat buffer; the k-th also all-reduces and steps the optimiser
+        self.accum = max(1, int(accumulation_steps))
+        self._micro = 0
         self.graph = None
         self.static_x = self.static_y = None
         self._copy_stream = None
@@ -128,6 +138,8 @@ class DataParallelTrainer:
     def _early_hook(self, _param):
         # called by autograd right after the sentinel's gradient was accumulated: everything in the
         # early bucket is final -> reduce it on the side stream while the encoder backward continues
+        if self.accum > 1:
+            return  # accumulating: buckets are reduced once, after the last micro-step
         self._join_wgrads()
         self.fp.gather_grads("early")
         cur = torch.cuda.current_stream()
@@ -179,9 +191,20 @@ class DataParallelTrainer:
             out = self.model(x)
         logits = out[0] if isinstance(out, tuple) else out
         loss = self.loss_fn(logits.float(), y)
-        loss.backward()
-        self.allreduce_grads()
-        self.opt.step(grad_scale=1.0 / self.world)
+        if self.accum == 1:
+            loss.backward()
+            self.allreduce_grads()
+            self.opt.step(grad_scale=1.0 / self.world)
+        else:
+            (loss / self.accum).backward()
+            self._join_wgrads()
+            self.fp.gather_grads("all", accumulate=self._micro % self.accum != 0)
+            self._micro += 1
+            if self._micro % self.accum == 0:
+                if self.world > 1:
+                    for t in self.fp.buckets():
+                        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
+                self.opt.step(grad_scale=1.0 / self.world)
         metrics = self.metrics_fn(logits.detach(), y) if self.metrics_fn is not None else None
         return loss.detach(), metrics
 
@@ -193,6 +216,8 @@ class DataParallelTrainer:
     # -- CUDA-graph path ---------------------------------------------------------------------------
     def capture(self, x_example, y_example, warmup=3):
         """Captures the whole step in one CUDA graph (static input buffers)."""
+        if self.accum > 1:
+            raise RuntimeError("capture() with gradient accumulation is not supported: use step() (eager launches)")
         self.static_x = x_example.clone()
         self.static_y = y_example.clone()
         # the step's main chain is captured on a HIGH-priority stream: the side-stream weight gradients (default priority,
@@ -216,8 +241,15 @@ class DataParallelTrainer:
             self.static_x.copy_(x, non_blocking=True)
         if y is not None:
             self.static_y.copy_(y, non_blocking=True)
+        self._sync_hyper()
         self.graph.replay()
         return self.loss
+
+    def _sync_hyper(self):
+        # a scheduler (ReduceLROnPlateau, train_unet.py:381,442) edits param_groups between steps: push lr to the device word
+        sync = getattr(self.opt, "sync_hyper", None)
+        if sync is not None:
+            sync()
 
     # -- input pipeline: the next batch crosses PCIe while the current step computes -----------------
     def prefetch(self, x_host, y_host):
@@ -246,5 +278,6 @@ class DataParallelTrainer:
         self.static_x.copy_(self._stage[0])
         self.static_y.copy_(self._stage[1])
         self._stage_free.record(cur)
+        self._sync_hyper()
         self.graph.replay()
         return self.loss

@@ -722,26 +722,106 @@ def cross_entropy_rows(logits, labels):
 
 
 # --------------------------------------------------------------------------- fused AdamW on flat buffers
-class FlatAdamW:
-    """AdamW (train_unet.py:378) over one flat fp32 parameter/gradient buffer; graph-capturable."""
+class FlatAdamW(torch.optim.Optimizer):
+    """AdamW (train_unet.py:378) over one flat fp32 parameter/gradient buffer; graph-capturable.
 
-    def __init__(self, flat_param, flat_grad, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+    A ``torch.optim.Optimizer`` so that the reference's ``ReduceLROnPlateau(optimizer, mode='max', ...)``
+    (train_unet.py:381, 442) drives it unchanged, and with the wire format of ``torch.optim.AdamW.state_dict()`` so that
+    the reference's checkpoints (train_unet.py:477-486) load into it and vice versa: pass ``named_params`` (the model's
+    trainable parameters in ``model.parameters()`` order) and ``offsets`` {name: (offset, numel)} into the flat buffer.
+    The learning rate lives in device memory (``hyper[0]``): changing ``param_groups[0]['lr']`` takes effect at the next
+    ``step()`` / ``sync_hyper()`` even inside a captured graph; betas / eps / weight_decay are launch constants."""
+
+    def __init__(self, flat_param, flat_grad, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, named_params=None, offsets=None):
         _require_cuda(flat_param, flat_grad)
+        self.named = list(named_params) if named_params is not None else None
+        self.offsets = offsets
+        defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False, foreach=None,
+                        capturable=False, differentiable=False, fused=None)
+        super().__init__([q for _, q in self.named] if self.named else [flat_param], defaults)
         self.p, self.g = flat_param, flat_grad
         self.m = torch.zeros_like(flat_param)
         self.v = torch.zeros_like(flat_param)
-        self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
         self.step_count = torch.zeros((), dtype=torch.int64, device=flat_param.device)
         self.hyper = torch.tensor([lr, 1.0, 1.0, 0.0], dtype=torch.float32, device=flat_param.device)
+        self._lr_on_device = float(lr)
+
+    # kept for callers that predate param_groups
+    @property
+    def betas(self):
+        return self.param_groups[0]["betas"]
+
+    @property
+    def eps(self):
+        return self.param_groups[0]["eps"]
+
+    @property
+    def weight_decay(self):
+        return self.param_groups[0]["weight_decay"]
 
     def set_lr(self, lr: float):
-        self.hyper[0] = lr
+        self.param_groups[0]["lr"] = float(lr)
+        self.sync_hyper()
 
-    def step(self, grad_scale: float = 1.0):
+    def sync_hyper(self):
+        """Pushes param_groups[0]['lr'] to the device word the (possibly graph-captured) kernels read."""
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_on_device:
+            self.hyper[0:1].fill_(lr)
+            self._lr_on_device = lr
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0):
         L = _lib.load()
-        check(L.b200_adamw_prepare(_ptr(self.step_count), self.betas[0], self.betas[1], _ptr(self.hyper), _stream()), "adamw_prepare")
+        self.sync_hyper()
+        g = self.param_groups[0]
+        check(L.b200_adamw_prepare(_ptr(self.step_count), g["betas"][0], g["betas"][1], _ptr(self.hyper), _stream()), "adamw_prepare")
         check(
             L.b200_adamw_flat(_ptr(self.p), _ptr(self.g), _ptr(self.m), _ptr(self.v), self.p.numel(), _ptr(self.hyper),
-                              self.betas[0], self.betas[1], self.eps, self.weight_decay, float(grad_scale), _stream()),
+                              g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], float(grad_scale), _stream()),
             "adamw_flat",
         )
+
+    # ---- torch.optim.AdamW wire format ------------------------------------------------------------------------------
+    def _slices(self):
+        if self.named is None or self.offsets is None:
+            raise RuntimeError("FlatAdamW: state_dict()/load_state_dict() need named_params and offsets")
+        return [(q, *self.offsets[n]) for n, q in self.named]
+
+    def state_dict(self):
+        step = float(self.step_count.item())
+        state = {}
+        if step > 0:
+            for i, (q, off, k) in enumerate(self._slices()):
+                state[i] = {"step": torch.tensor(step), "exp_avg": self.m[off:off + k].view_as(q).clone(),
+                            "exp_avg_sq": self.v[off:off + k].view_as(q).clone()}
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        group["params"] = list(range(len(self.named)))
+        return {"state": state, "param_groups": [group]}
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        slices = self._slices()
+        groups = state_dict["param_groups"]
+        ids = [i for g in groups for i in g["params"]]
+        if len(ids) != len(slices):
+            raise ValueError(f"loaded state dict has {len(ids)} parameters, this optimizer has {len(slices)}")
+        self.m.zero_()
+        self.v.zero_()
+        step = 0.0
+        for (q, off, k), i in zip(slices, ids):
+            st = state_dict["state"].get(i)
+            if st is None:
+                continue
+            if tuple(st["exp_avg"].shape) != tuple(q.shape):
+                raise ValueError(f"optimizer state {i}: shape {tuple(st['exp_avg'].shape)} does not match parameter {tuple(q.shape)}")
+            self.m[off:off + k].copy_(st["exp_avg"].reshape(-1))
+            self.v[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+            step = max(step, float(st["step"]))
+        self.step_count.fill_(int(step))
+        g0 = groups[0]
+        for key in ("lr", "betas", "eps", "weight_decay"):
+            if key in g0:
+                self.param_groups[0][key] = tuple(g0[key]) if key == "betas" else g0[key]
+        self._lr_on_device = None
+        self.sync_hyper()

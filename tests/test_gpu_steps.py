@@ -215,3 +215,99 @@ def test_dp_trainer_single_gpu_matches_manual_step(cuda_dev):
         assert la == lb_t.item()
     with pytest.raises(RuntimeError):
         DataParallelTrainer(UNet3D(1, 4).cuda(), M.combined_loss).prefetch(xh, yh)
+
+
+# --------------------------------------------------------------------------------- §8f-1/2: optimiser wire format, scheduler, accumulation
+def _skip_zero_grad_bias(k):
+    return k.endswith("double_conv.0.bias") or k.endswith("double_conv.4.bias")
+
+
+@pytest.mark.gpu
+def test_reference_checkpoint_continues_training(cuda_dev, golden_dir):
+    """A checkpoint written by the reference after two AdamW steps (model + optimizer state) is loaded into the drop-in
+    model + FlatAdamW; the third step on the GPU lands on the parameters the reference has after ITS third step."""
+    import os
+    from multimodal_segmentation_project_b200.checkpoint import load_checkpoint, save_checkpoint
+    nxt = np.load(os.path.join(golden_dir, "ref_checkpoint_next_step.npz"))
+    net = UNet3D(1, 4, features=[8, 16], dropout_rate=0.0).cuda().train()
+    tr = DataParallelTrainer(net, M.combined_loss, lr=5e-4, weight_decay=0.0, autocast_dtype=None)   # overwritten by the checkpoint
+    ckpt = load_checkpoint(os.path.join(golden_dir, "ref_checkpoint_f8_16.pth"), net, tr.opt, map_location="cuda")
+    assert tr.opt.param_groups[0]["lr"] == 1e-3 and tr.opt.param_groups[0]["weight_decay"] == 1e-2
+    assert int(tr.opt.step_count.item()) == 2
+    sd_opt = tr.opt.state_dict()   # round trip of the wire format
+    ref_opt = ckpt["optimizer_state_dict"]
+    assert len(sd_opt["state"]) == len(ref_opt["state"]) == 46
+    for i in ref_opt["state"]:
+        assert torch.equal(sd_opt["state"][i]["exp_avg"].cpu(), ref_opt["state"][i]["exp_avg"].cpu())
+        assert torch.equal(sd_opt["state"][i]["exp_avg_sq"].cpu(), ref_opt["state"][i]["exp_avg_sq"].cpu())
+        assert float(sd_opt["state"][i]["step"]) == 2.0
+    loss = tr.step(torch.from_numpy(nxt["x"]).cuda(), torch.from_numpy(nxt["y"]).cuda())
+    assert abs(loss.item() - float(nxt["loss"])) <= 2e-5
+    sd = net.state_dict()
+    a = torch.cat([sd[k].flatten().cpu() for k, _ in net.named_parameters() if not _skip_zero_grad_bias(k)])
+    b = torch.cat([torch.from_numpy(nxt["after/" + k]).flatten() for k, _ in net.named_parameters() if not _skip_zero_grad_bias(k)])
+    close = ((a - b).abs() <= 2e-6 + 1e-4 * b.abs()).float().mean().item()
+    assert close >= 0.999 and rel_l2(a, b) <= 1e-4, (close, rel_l2(a, b))
+    for k in ("encoder.0.double_conv.1.running_mean", "bottleneck.double_conv.5.running_var"):
+        assert rel_l2(sd[k].cpu(), torch.from_numpy(nxt["after/" + k])) <= 1e-5
+    # and back: what we save loads into a plain torch.optim.AdamW over a same-shaped model (the reference's optimizer)
+    import io
+    buf = io.BytesIO()
+    save_checkpoint(buf, net, tr.opt, epoch=26, val_dice=0.5)
+    buf.seek(0)
+    twin = UNet3D(1, 4, features=[8, 16], dropout_rate=0.0)
+    topt = torch.optim.AdamW(twin.parameters())
+    obj = load_checkpoint(buf, twin, topt, map_location="cpu")
+    assert obj["epoch"] == 26 and float(topt.state_dict()["state"][0]["step"]) == 3.0
+    assert abs(float(np.abs(topt.state_dict()["state"][0]["exp_avg"].numpy() - nxt["exp_avg_0"]).max())) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_reduce_lr_on_plateau_drives_flat_adamw(cuda_dev):
+    """train_unet.py:381,442: ReduceLROnPlateau(optimizer, mode='max', patience, factor, min_lr) + scheduler.step(val_dice);
+    the new rate reaches the captured graph through the device-side hyper-parameter word."""
+    sd = init_state_dict(1, 4, seed=0)
+    x, y = structured_volume(2, 16, seed=5)
+    xc, yc = x.cuda(), y.cuda()
+    net = UNet3D(1, 4, dropout_rate=0.0).cuda(); net.load_state_dict(sd); net.train()
+    tr = DataParallelTrainer(net, M.combined_loss, lr=1e-3, autocast_dtype=None)
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(tr.opt, mode="max", patience=1, factor=0.1, min_lr=1e-6)
+    tr.capture(xc, yc, warmup=1)
+    before = net.final_conv.weight.detach().clone()
+    tr.replay()
+    d1 = (net.final_conv.weight.detach() - before).abs().max().item()
+    for _ in range(3):
+        sched.step(0.5)                       # no improvement -> lr 1e-3 -> 1e-4
+    assert abs(tr.opt.param_groups[0]["lr"] - 1e-4) < 1e-12
+    before = net.final_conv.weight.detach().clone()
+    tr.replay()
+    d2 = (net.final_conv.weight.detach() - before).abs().max().item()
+    assert abs(tr.opt.hyper[0].item() - 1e-4) < 1e-10
+    assert 0.05 * d1 < d2 < 0.2 * d1, (d1, d2)   # Adam's first steps move by ~lr
+
+
+@pytest.mark.gpu
+def test_gradient_accumulation_matches_large_batch(cuda_dev):
+    """accelerator.accumulate (train_unet.py:221): two micro-steps of loss/2 then one optimiser step == torch AdamW on the
+    mean of the two micro-batch losses (BatchNorm statistics stay per micro-batch, as in the reference)."""
+    sd = init_state_dict(1, 4, seed=0)
+    x, y = structured_volume(4, 16, seed=9)
+    xa, ya, xb, yb = x[:2].cuda(), y[:2].cuda(), x[2:].cuda(), y[2:].cuda()
+    ref = UNet3D(1, 4, dropout_rate=0.0).cuda(); ref.load_state_dict(sd); ref.train()
+    opt = torch.optim.AdamW(ref.parameters(), lr=1e-3, weight_decay=1e-2)
+    opt.zero_grad()
+    (M.combined_loss(ref(xa), ya) / 2).backward()
+    (M.combined_loss(ref(xb), yb) / 2).backward()
+    opt.step()
+    net = UNet3D(1, 4, dropout_rate=0.0).cuda(); net.load_state_dict(sd); net.train()
+    tr = DataParallelTrainer(net, M.combined_loss, lr=1e-3, weight_decay=1e-2, autocast_dtype=None, accumulation_steps=2)
+    w0 = net.final_conv.weight.detach().clone()
+    tr.step(xa, ya)
+    assert torch.equal(net.final_conv.weight.detach(), w0)      # no optimiser step on the first micro-step
+    tr.step(xb, yb)
+    a = torch.cat([q.detach().flatten() for k, q in net.named_parameters() if not _skip_zero_grad_bias(k)])
+    b = torch.cat([q.detach().flatten() for k, q in ref.named_parameters() if not _skip_zero_grad_bias(k)])
+    close = ((a - b).abs() <= 1e-5 + 1e-4 * b.abs()).float().mean().item()
+    assert close >= 0.999 and rel_l2(a, b) <= 1e-3, (close, rel_l2(a, b))
+    with pytest.raises(RuntimeError):
+        tr.capture(xa, ya)
