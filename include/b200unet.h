@@ -234,6 +234,20 @@ int b200_adamw_prepare(int64_t* step, float beta1, float beta2, float* hyper, vo
 int b200_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float beta1,
                     float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 
+/* ---- device-side input pipeline: utils/dataloader.py:111-117 (CT window), :128-145 (MRI z-score, 1st-99th
+ * percentile clip, min-max), :162-181 (AMOS / CHAOS label remaps) on tensors already in HBM --------------------------------- */
+int b200_ct_window(const float* x, float* y, int64_t n, float lo, float hi, void* stream);
+int64_t b200_preprocess_workspace_bytes(void);
+/* out[0] = mean, out[1] = population variance of x (fp64, device memory); fixed-order fp64 accumulation */
+int b200_moments_f32(const float* x, int64_t n, void* workspace, double* out, void* stream);
+/* values[r] = element of 0-based rank ranks[r] in ascending order (exact order statistic, 3-pass radix select, no host sync) */
+int b200_select_ranks_f32(const float* x, int64_t n, const int64_t* ranks, int nranks, float* values, void* workspace, void* stream);
+/* params (fp64, device): mean, std + 1e-8 (float32 values), low, high, high - low + 1e-8: numpy's dtype flow of preprocess_mri */
+int b200_mri_normalize(const float* x, float* y, int64_t n, const double* params, void* stream);
+/* out = 0, then for each range in order: lo <= in <= hi -> val (host arrays, <= 8 ranges); out_u8: write uint8 instead of int64 */
+int b200_label_remap(const int64_t* in, void* out, int64_t n, const int64_t* lo, const int64_t* hi, const int64_t* val, int nranges,
+                     int out_u8, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,12 @@ def _declare(lib) -> None:
         "b200_channel_sum": (I, [I, P, L, I, P, P, P]),
         "b200_maxpool2_fwd": (I, [I, P, P, I, I, I, I, I, P]),
         "b200_maxpool2_bwd": (I, [I, P, P, P, I, I, I, I, I, P]),
+        "b200_ct_window": (I, [P, P, L, F, F, P]),
+        "b200_preprocess_workspace_bytes": (L, []),
+        "b200_moments_f32": (I, [P, L, P, P, P]),
+        "b200_select_ranks_f32": (I, [P, L, P, I, P, P, P]),
+        "b200_mri_normalize": (I, [P, P, L, P, P]),
+        "b200_label_remap": (I, [P, P, L, P, P, P, I, I, P]),
         "b200_maxpool2_bwd_add": (I, [I, P, P, P, P, I, I, I, I, I, P]),
         "b200_convt2_fwd": (I, [I, P, P, P, P, I, I, I, I, I, I, P]),
         "b200_convt2_bwd_data": (I, [I, P, P, P, I, I, I, I, I, I, P]),
