@@ -21,7 +21,10 @@ import sys
 import threading
 import time
 
-# rank 0 prints exactly one JSON line on stdout: NCCL's banner / debug output (whatever NCCL_DEBUG the box exports) goes to stderr
+# rank 0 prints exactly one JSON line on stdout: NCCL's banner / debug output goes to stderr.  NCCL honours NCCL_DEBUG_FILE only
+# above the VERSION level, so a box that exports NCCL_DEBUG=VERSION (banner on stdout) is raised to WARN; INFO/TRACE are kept.
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import torch
