@@ -209,7 +209,7 @@ def run_ours(args):
     peaks = _peaks()
 
     torch.manual_seed(0)
-    model = UNet3D(in_channels=1, out_channels=CLASSES, dropout_rate=0.0).to(dev).train()
+    model = UNet3D(in_channels=1, out_channels=CLASSES, dropout_rate=args.dropout).to(dev).train()
     trainer = DataParallelTrainer(model, M.combined_loss, lr=1e-3, autocast_dtype=torch.bfloat16,
                                   metrics_fn=lambda lg, y: F.confusion_counts(lg, y))
     x_h, y_h = structured_volume(BATCH_PER_GPU, PATCH, seed=1234 + rank)
@@ -337,6 +337,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.0, help="Dropout3d rate (BASELINE config: 0.0; the reference's constructor default is 0.1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
