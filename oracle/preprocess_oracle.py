@@ -33,26 +33,21 @@ def preprocess(image: np.ndarray, dataset_name: str) -> np.ndarray:
     return preprocess_ct(image) if dataset_name.lower().endswith("_ct") else preprocess_mri(image)
 
 
+# CHAOS label images store organs as grey levels; the reference accepts a band around each nominal level
+# (utils/dataloader.py:169-180): nominal level -> (lowest, highest) accepted value
+CHAOS_BANDS = {0: (0, 0), 63: (55, 70), 126: (110, 135), 189: (175, 200), 252: (240, 255)}
+
+
 def remap_labels(label: np.ndarray, dataset_name: str) -> np.ndarray:
-    """utils/dataloader.py:162-185"""
+    """utils/dataloader.py:162-185 — table form: every (band -> class) rule is applied in the dictionary's order onto a
+    zero-initialised volume, so a later rule would override an earlier one exactly as the reference's masked stores do."""
     if dataset_name.startswith("amos"):
-        new = np.zeros_like(label)
-        for old, idx in AMOS_MAPPING.items():
-            new[label == old] = idx
-        return new
-    if dataset_name.startswith("chaos"):
-        new = np.zeros_like(label)
-        for old, val in CHAOS_MAPPING.items():
-            if old == 63:
-                mask = (label >= 55) & (label <= 70)
-            elif old == 126:
-                mask = (label >= 110) & (label <= 135)
-            elif old == 189:
-                mask = (label >= 175) & (label <= 200)
-            elif old == 252:
-                mask = (label >= 240) & (label <= 255)
-            else:
-                mask = label == 0
-            new[mask] = val
-        return new
-    return label
+        rules = [((old, old), new) for old, new in AMOS_MAPPING.items()]
+    elif dataset_name.startswith("chaos"):
+        rules = [(CHAOS_BANDS[old], new) for old, new in CHAOS_MAPPING.items()]
+    else:
+        return label  # 'ts*' and 'btcv' already use the target convention
+    out = np.zeros_like(label)
+    for (lo, hi), new in rules:
+        out[(label >= lo) & (label <= hi)] = new
+    return out
