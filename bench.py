@@ -268,15 +268,20 @@ def run_ours(args):
 
     # ---- end to end through the public API: pinned host inputs, loss read back every step -------
     # With the captured step the trainer's input pipeline is used: every step's batch is copied from pinned host memory
-    # inside the timed region (K copies for K steps), step i+1's copy overlapping step i's kernels on a copy stream.
+    # inside the timed region (K copies for K steps), step i+1's copy overlapping step i's kernels on a copy stream, and
+    # every step's loss is copied to the host and read there (K reads), one step behind the GPU.
     def e2e_loop(n):
         if use_graph:
             trainer.prefetch(x_h, y_h)
+            pending = None
             for i in range(n):
-                l = trainer.replay_prefetched()
+                h = trainer.replay_prefetched_async()   # step i: staged batch -> graph -> loss copied to pinned host memory
                 if i + 1 < n:
-                    trainer.prefetch(x_h, y_h)
-                l.item()  # device -> host read of the step's result
+                    trainer.prefetch(x_h, y_h)          # step i+1's batch crosses PCIe while step i computes
+                if pending is not None:
+                    pending.value()                     # host reads step i-1's loss while step i runs
+                pending = h
+            pending.value()
         else:
             for _ in range(n):
                 step_e2e().item()

@@ -96,6 +96,17 @@ class FlatParams:
                 torch._foreach_copy_(dst, src)
 
 
+class _LossHandle:
+    """Loss of one step on its way to the host (pinned slot + completion event)."""
+
+    def __init__(self, host, event):
+        self._host, self._event = host, event
+
+    def value(self) -> float:
+        self._event.synchronize()
+        return float(self._host)
+
+
 class DataParallelTrainer:
     """step(x, y) = zero_grad -> forward -> loss -> backward -> all-reduce(sum) -> AdamW(grad/world)."""
 
@@ -244,6 +255,20 @@ class DataParallelTrainer:
         self._sync_hyper()
         self.graph.replay()
         return self.loss
+
+    def replay_prefetched_async(self):
+        """replay_prefetched() + an asynchronous device -> host copy of the step's loss into pinned memory.  Returns a handle
+        whose .value() blocks until THAT step's loss has landed: read it while the next step is already running."""
+        loss = self.replay_prefetched()
+        if getattr(self, "_loss_ring", None) is None:
+            self._loss_ring = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._loss_events = [torch.cuda.Event() for _ in range(4)]
+            self._loss_slot = 0
+        i = self._loss_slot
+        self._loss_slot = (i + 1) % len(self._loss_ring)
+        self._loss_ring[i].copy_(loss, non_blocking=True)
+        self._loss_events[i].record(torch.cuda.current_stream())
+        return _LossHandle(self._loss_ring[i], self._loss_events[i])
 
     def _sync_hyper(self):
         # a scheduler (ReduceLROnPlateau, train_unet.py:381,442) edits param_groups between steps: push lr to the device word

@@ -337,3 +337,23 @@ def test_train_step_is_run_to_run_deterministic(cuda_dev, dtype):
     assert torch.equal(o1, o2) and torch.equal(l1, l2)
     differ = [k for k in g1 if not torch.equal(g1[k], g2[k])]
     assert not differ, differ
+
+
+@pytest.mark.gpu
+def test_async_loss_readback_matches_sync(cuda_dev):
+    sd = init_state_dict(1, 4, seed=0)
+    x, y = structured_volume(2, 16, seed=41)
+    xc, yc = x.cuda(), y.cuda()
+    xh, yh = x.pin_memory(), y.pin_memory()
+    na = UNet3D(1, 4, dropout_rate=0.0).cuda(); na.load_state_dict(sd); na.train()
+    nb = UNet3D(1, 4, dropout_rate=0.0).cuda(); nb.load_state_dict(sd); nb.train()
+    ta = DataParallelTrainer(na, M.combined_loss, autocast_dtype=None); ta.capture(xc, yc, warmup=1)
+    tb = DataParallelTrainer(nb, M.combined_loss, autocast_dtype=None); tb.capture(xc, yc, warmup=1)
+    want = [ta.replay(xh, yh).item() for _ in range(6)]
+    tb.prefetch(xh, yh)
+    handles = []
+    for i in range(6):
+        handles.append(tb.replay_prefetched_async())
+        if i < 5:
+            tb.prefetch(xh, yh)
+    assert [h.value() for h in handles[-4:]] == want[-4:]     # ring of 4 slots: the last four are still valid
