@@ -18,6 +18,7 @@
 #include "tc_ptx.cuh"
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -256,25 +257,29 @@ conv3d_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tm0, co
   if (warp == 1) tc::tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-// out[nchunk][slab][kh][kw][kc(2)][kd(3)][n(n_tile)][8]
-__global__ void pack_k3_tc2_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout_f, int Cin_f, int dgrad, int n_tile, int slabs,
-                                   int64_t total) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t t = i;
-    const int j = (int)(t % 8); t /= 8;
-    const int nn = (int)(t % n_tile); t /= n_tile;
-    const int kd = (int)(t % 3); t /= 3;
-    const int kc = (int)(t % 2); t /= 2;
-    const int khw = (int)(t % 9); t /= 9;
-    const int slab = (int)(t % slabs);
-    const int nchunk = (int)(t / slabs);
-    const int tap = kd * 9 + khw;
-    const int k = slab * 16 + kc * 8 + j;
-    const int o = nchunk * n_tile + nn;
-    float v;
-    if (!dgrad) v = w[((int64_t)o * Cin_f + k) * 27 + tap];
-    else v = w[((int64_t)k * Cin_f + o) * 27 + (26 - tap)];
-    out[i] = __float2bfloat16_rn(v);
+// out[nchunk][slab][kh][kw][kc(2)][kd(3)][n(n_tile)][8]: one thread builds one 16-byte group (8 consecutive k).  Threads are
+// numbered with the filter tap fastest, so that neighbouring threads read neighbouring floats of w (the 27 taps of one
+// (o, k) pair are contiguous); the index is decomposed once per group in 32-bit arithmetic (the first version did six
+// 64-bit div/mod per ELEMENT and cost 0.14 ms per step).
+__global__ void __launch_bounds__(256) pack_k3_tc2_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout_f, int Cin_f, int dgrad,
+                                                          int n_tile_i, int slabs_i, int64_t total) {
+  const uint32_t groups = (uint32_t)(total / 8), n_tile = (uint32_t)n_tile_i, slabs = (uint32_t)slabs_i;
+  for (uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < groups; gid += gridDim.x * blockDim.x) {
+    uint32_t t = gid;
+    const uint32_t tap = t % 27; t /= 27;
+    const uint32_t kc = t % 2; t /= 2;
+    const uint32_t nn = t % n_tile; t /= n_tile;
+    const uint32_t slab = t % slabs;
+    const uint32_t nchunk = t / slabs;
+    const uint32_t kd = tap / 9, khw = tap % 9, k0 = slab * 16 + kc * 8, o = nchunk * n_tile + nn;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      f[j] = !dgrad ? w[((int64_t)o * Cin_f + (k0 + j)) * 27 + tap] : w[((int64_t)(k0 + j) * Cin_f + o) * 27 + (26 - tap)];
+    Vec8<bf16> v;
+    v.set(f);
+    const uint32_t g = ((((nchunk * slabs + slab) * 9 + khw) * 2 + kc) * 3 + kd) * n_tile + nn;
+    v.store(out + (int64_t)g * 8);
   }
 }
 
@@ -353,7 +358,7 @@ int b200_pack_conv3_weights_tc2(int mode, const float* w, void* out, int Cout, i
                "pack_conv3_weights(tc2): channel counts %d -> %d not supported by the tcgen05 path", conv_in, conv_out);
   const int n_tile = n_tile_for(conv_out), slabs = conv_in / 16;
   const int64_t total = (int64_t)27 * Cin * Cout;
-  pack_k3_tc2_kernel<<<b200_grid_for(total, 256, B200_NUM_SMS * 8), 256, 0, stream>>>(w, (bf16*)out, Cout, Cin, dgrad, n_tile, slabs, total);
+  pack_k3_tc2_kernel<<<b200_grid_for(total / 8, 256, B200_NUM_SMS * 4), 256, 0, stream>>>(w, (bf16*)out, Cout, Cin, dgrad, n_tile, slabs, total);
   B200_CHECK_LAUNCH("pack_conv3_weights_tc2");
   return B200_OK;
 }
