@@ -113,3 +113,45 @@ def test_flat_params_layout_and_buckets():
         p.requires_grad = False
     fp2 = FlatParams(net2)
     assert fp2.early_sentinel is None and len(fp2.buckets()) == 1
+
+
+def _accum_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = _Tiny()
+    tr = DataParallelTrainer(model, _loss, autocast_dtype=None, optimizer_factory=lambda fp: _TorchFlatAdamW(fp), accumulation_steps=2)
+    before = tr.fp.flat.detach().clone()
+    for micro in range(4):                                   # two optimiser steps of two micro-batches each
+        g = torch.Generator().manual_seed(1000 + 10 * micro + rank)
+        x = torch.randn(2, 1, 6, 6, 6, generator=g)
+        y = torch.randint(0, 3, (2, 1, 6, 6, 6), generator=g)
+        tr.step(x, y)
+        if micro == 0:
+            assert torch.equal(tr.fp.flat, before), "no optimiser step (and no all-reduce) on a non-boundary micro-step"
+    out[rank] = tr.fp.flat.detach().clone()
+    dist.destroy_process_group()
+
+
+def test_gradient_accumulation_two_ranks_gloo():
+    """accelerator.accumulate semantics (train_unet.py:221) on two ranks: per optimiser step the update uses the mean over
+    ranks of the mean over micro-batches; ranks stay identical."""
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_accum_worker, args=(2, port, out), nprocs=2, join=True)
+    assert torch.equal(out[0], out[1])
+    torch.manual_seed(0)
+    model = _Tiny()
+    fp = FlatParams(model)
+    opt = _TorchFlatAdamW(fp)
+    for step in range(2):
+        fp.zero_grad()
+        for micro in (2 * step, 2 * step + 1):
+            for rank in range(2):
+                g = torch.Generator().manual_seed(1000 + 10 * micro + rank)
+                x = torch.randn(2, 1, 6, 6, 6, generator=g)
+                y = torch.randint(0, 3, (2, 1, 6, 6, 6), generator=g)
+                (_loss(model(x), y) / 4).backward()
+        opt.step(1.0)
+    assert torch.allclose(fp.flat, out[0], rtol=1e-5, atol=1e-7)
