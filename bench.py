@@ -168,7 +168,7 @@ def run_reference(args):
 
 # ================================================================================ this repo's arm (GPU)
 def time_top_conv_kernel(dev, iters=20):
-    """CUDA-event time of the dominant kernel: conv3d_tc2_kernel on decoder.3.c0's fprop shape
+    """CUDA-event time of the dominant kernel: conv3d_tc3_kernel (the persistent tcgen05 convolution) on decoder.3.c0's fprop shape
     (2 x 128^3, (16+16) -> 16 channels, 115.96 GFLOP), L2 flushed between launches."""
     from multimodal_segmentation_project_b200 import _lib, functional as F
     N, S, c0, c1, cout = BATCH_PER_GPU, PATCH, 16, 16, 16
@@ -305,11 +305,11 @@ def run_ours(args):
     # ---- roofline of the dominant kernel + CPU baseline (rank 0, N = 1 only for the CPU leg) -----
     k_ms, k_flops = time_top_conv_kernel(dev)
     achieved = k_flops / (k_ms / 1e3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "conv3d_tc2_kernel (decoder.3.c0 fprop, 2x128^3, (16+16)->16 ch, 115.96 GFLOP/launch)", "achieved": achieved,
+    roofline = {"bound": "tensor", "kernel": "conv3d_tc3_kernel (persistent; decoder.3.c0 fprop, 2x128^3, (16+16)->16 ch, 115.96 GFLOP/launch)", "achieved": achieved,
                 "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"],
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this shape from one `ncu --set full` capture
-                # (profiles/r01_ncu_final_kernels_summary.md): 268.9 MB + 103.5 MB; algorithmic bytes are 268.4 in + 134.2 out
-                "traffic": 372373504, "traffic_unit": "bytes/launch",
+                # (profiles/r01_ncu_final_kernels_summary.md): 268.6 MB + 105.6 MB; algorithmic bytes are 268.4 in + 134.2 out
+                "traffic": 374207232, "traffic_unit": "bytes/launch",
                 "peak_source": peaks["source"] + " bf16 burst (kernel timed alone)", "kernel_ms": k_ms,
                 "step_conv_tflops_vs_sustained": (F_TRAIN_PER_VOXEL * vox_step / world / (ms / args.steps / 1e3) / 1e12) / peaks["bf16_sustained"]}
     cpu = None

@@ -94,7 +94,8 @@ int64_t b200_pack_conv3_bytes(int mode, int dtype, int Cout, int Cin);
  * 2 (tcgen05, B200_PACK_*_TC weights); the caller packs the weights accordingly. */
 int b200_conv3d_k3_select(int dtype, int impl, int c0, int c1, int co0, int co1, int N, int D, int H, int W);
 /* selects the persistent tcgen05 convolution (one CTA per SM looping over tiles, double-buffered TMEM):
- * 0 never, 1 auto (default), 2 whenever the layer has enough tiles — for tests and benchmarks. */
+ * 0 never, 1 auto (default: every layer with >= 2 tiles per SM and <= 64 output channels per tile), 2 same as 1,
+ * 3 only 16->16 layers — for tests and benchmarks. */
 int b200_set_conv_persistent(int mode);
 int b200_conv3d_k3(int dtype, int impl, const void* x0, int c0, const void* x1, int c1,
                    const void* wpack, const float* bias, void* y0, int co0, void* y1, int co1,

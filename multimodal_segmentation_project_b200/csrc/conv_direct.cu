@@ -609,11 +609,14 @@ extern "C" int b200_conv3d_k3(int dtype, int impl, const void* x0, int c0, const
     B200_REQUIRE(b200_conv3d_k3_tc_supported(c0, c1, co0, co1, N, D, H, W), B200_ERR_UNSUPPORTED,
                  "conv3d_k3(tcgen05): channels (%d+%d)->(%d+%d) need multiples of 16 (Cout <= 128 or a multiple of 128)", c0, c1, co0, co1);
     if (tc_version() == 2) {
-      // The persistent kernel (conv_tc3.cu) is within a few % of the two-CTA-per-SM kernel: both are bound by the
-      // tensor core's serialized operand fetch (T_mma ~ A wavefronts + B wavefronts + N/2).  It wins
-      // for single-slab 16-channel layers (2048 tiles, 120.9 vs 129.0 us at 2x128^3) and is used only there by default.
+      // The persistent kernel (conv_tc3.cu) and the two-CTA-per-SM kernel (conv_tc2.cu) are both bound by the tensor core's
+      // serialized operand fetch (T_mma ~ A wavefronts + B wavefronts + N/2).
+      // In isolation the two kernels are within a few percent of each other except for 16->16 (persistent: 121 vs 129 us);
+      // inside the train step, where the side-stream weight gradients compete for the SMs, the persistent kernel is the
+      // better neighbour for every layer with enough tiles (A/B on one box: 4.91 -> 4.79..4.87 ms/step), so "auto" uses it
+      // wherever b200_conv3d_k3_tc3_wanted() says the layer has >= 2 tiles per SM.  Mode 3 = the old 16->16-only policy.
       if (g_conv_persistent < 0) { const char* e = getenv("B200_CONV_PERSISTENT"); g_conv_persistent = e ? atoi(e) : 1; }
-      const bool want = g_conv_persistent == 2 || (g_conv_persistent == 1 && c0 + c1 == 16 && co0 + co1 == 16);
+      const bool want = g_conv_persistent == 1 || g_conv_persistent == 2 || (g_conv_persistent == 3 && c0 + c1 == 16 && co0 + co1 == 16);
       if (want && b200_conv3d_k3_tc3_wanted(c0, c1, co0, co1, N, D, H, W))
         return b200_conv3d_k3_tc3(x0, c0, x1, c1, wpack, bias, y0, co0, y1, co1, N, D, H, W, st);
       return b200_conv3d_k3_tc2(x0, c0, x1, c1, wpack, bias, y0, co0, y1, co1, N, D, H, W, st);
@@ -645,7 +648,7 @@ extern "C" int b200_conv3d_k3(int dtype, int impl, const void* x0, int c0, const
 }
 
 extern "C" int b200_set_conv_persistent(int mode) {
-  B200_REQUIRE(mode >= 0 && mode <= 2, B200_ERR_UNSUPPORTED, "set_conv_persistent: mode must be 0 (never), 1 (auto) or 2 (whenever possible)");
+  B200_REQUIRE(mode >= 0 && mode <= 3, B200_ERR_UNSUPPORTED, "set_conv_persistent: mode must be 0 (never), 1 (auto), 2 (whenever possible) or 3 (16->16 only)");
   g_conv_persistent = mode;
   return B200_OK;
 }

@@ -217,7 +217,7 @@ def set_wgrad_impl(impl: int) -> None:
 
 
 def set_conv_persistent(mode: int) -> None:
-    """0 never, 1 auto, 2 whenever the layer has enough tiles (process-wide; tests and benchmarks)."""
+    """0 never, 1 auto (every layer with enough tiles), 2 same as 1, 3 only 16->16 layers (process-wide; tests and benchmarks)."""
     check(_lib.load().b200_set_conv_persistent(int(mode)), "set_conv_persistent")
 
 
