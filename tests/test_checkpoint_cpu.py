@@ -56,3 +56,30 @@ def test_saved_file_has_reference_keys_and_loads_into_torch_adamw():
     buf.seek(0)
     load_checkpoint(buf, net2, opt2)
     assert opt2.param_groups[0]["weight_decay"] == 1e-2
+
+
+def test_oracle_continues_reference_checkpoint():
+    """CPU pin of the whole chain: reference checkpoint -> oracle forward/backward (functional restatement) -> torch AdamW
+    with the checkpoint's optimizer state -> the parameters the reference itself has after its third step."""
+    import numpy as np
+    from oracle import metrics_oracle as OM
+    from oracle.unet_oracle import train_step_grads
+
+    ckpt = _ref_ckpt()
+    nxt = np.load(os.path.join(GOLD, "ref_checkpoint_next_step.npz"))
+    sd = {k: v.clone() for k, v in ckpt["model_state_dict"].items()}
+    x, y = torch.from_numpy(nxt["x"]), torch.from_numpy(nxt["y"])
+    loss, _, grads, new_buffers = train_step_grads(sd, x, y, OM.combined_loss)
+    assert abs(float(loss) - float(nxt["loss"])) <= 1e-6
+    names = [k for k in sd if k in grads]
+    params = [torch.nn.Parameter(sd[k].clone()) for k in names]
+    opt = torch.optim.AdamW(params, lr=123.0)            # hyper-parameters come from the checkpoint
+    opt.load_state_dict(ckpt["optimizer_state_dict"])
+    for p, k in zip(params, names):
+        p.grad = grads[k]
+    opt.step()
+    for p, k in zip(params, names):
+        if k.endswith("double_conv.0.bias") or k.endswith("double_conv.4.bias"):
+            continue  # pre-BatchNorm conv biases: their gradient is round-off noise around 0 and AdamW turns its SIGN into lr-sized steps
+        ref = torch.from_numpy(nxt["after/" + k])
+        assert torch.allclose(p.detach(), ref, rtol=1e-5, atol=2e-6), k
