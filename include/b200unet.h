@@ -107,6 +107,9 @@ int64_t b200_conv3d_wgrad_workspace(int c0, int c1, int Cout, int N, int D, int 
 /* process-wide selection of the weight-gradient kernel: 0 auto (tcgen05 for bf16 when the channel
  * counts allow), 1 CUDA-core split-K, 2 tcgen05 (error if unsupported) — for tests and benchmarks. */
 int b200_set_wgrad_impl(int impl);
+/* test hook: the next wide-row tcgen05 weight gradient returns B200_ERR_UNSUPPORTED without launching (checks that a
+ * failing kernel selection surfaces as an error instead of an uninitialised dw). */
+int b200_debug_fail_next_wgrad(int on);
 int b200_conv3d_wgrad(int dtype, const void* x0, int c0, const void* x1, int c1, const void* dy, int Cout,
                       float* dw, float* dbias, void* workspace, int64_t workspace_bytes,
                       int N, int D, int H, int W, void* stream);

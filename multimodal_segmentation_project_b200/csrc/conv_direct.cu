@@ -559,6 +559,7 @@ int64_t b200_conv3d_wgrad_tc3_workspace(int c0, int c1, int Cout, int N, int D, 
 int b200_conv3d_wgrad_tc3(const void* x0, int c0, const void* x1, int c1, const void* dy, int Cout, float* dw, void* workspace,
                           int N, int D, int H, int W, cudaStream_t stream);
 static int g_wgrad_impl = 0;  // 0 auto, 1 CUDA-core, 2 tcgen05
+static int g_inject_wgrad_failure = 0;  // tests: the next wide-row tcgen05 weight gradient reports failure
 // in_channels == 1 first layer (conv_stem.cu)
 bool b200_conv_stem_supported(int c0, int c1, int cout);
 bool b200_conv_stem_wgrad_supported(int c0, int c1, int cout);
@@ -653,6 +654,11 @@ extern "C" int b200_set_conv_persistent(int mode) {
   return B200_OK;
 }
 
+extern "C" int b200_debug_fail_next_wgrad(int on) {
+  g_inject_wgrad_failure = on ? 1 : 0;
+  return B200_OK;
+}
+
 extern "C" int b200_set_wgrad_impl(int impl) {
   B200_REQUIRE(impl >= 0 && impl <= 2, B200_ERR_UNSUPPORTED, "set_wgrad_impl: impl must be 0 (auto), 1 (CUDA-core) or 2 (tcgen05)");
   g_wgrad_impl = impl;
@@ -704,7 +710,9 @@ extern "C" int b200_conv3d_wgrad(int dtype, const void* x0, int c0, const void* 
     rc = b200_conv_stem_wgrad(dtype, x0, dy, Cout, dw, partial, N, D, H, W, st);
     if (rc) return rc;
   } else if (use_v3 && g_wgrad_impl != 1) {
-    rc = b200_conv3d_wgrad_tc3(x0, c0, x1, c1, dy, Cout, dw, partial, N, D, H, W, st);
+    rc = g_inject_wgrad_failure ? (g_inject_wgrad_failure = 0, b200_set_error("conv3d_wgrad: injected failure (b200_debug_fail_next_wgrad)"), B200_ERR_UNSUPPORTED)
+                                : b200_conv3d_wgrad_tc3(x0, c0, x1, c1, dy, Cout, dw, partial, N, D, H, W, st);
+    if (rc) return rc;
   } else if (tc_ok && g_wgrad_impl != 1) {
     rc = use_v2 ? b200_conv3d_wgrad_tc2(x0, c0, x1, c1, dy, Cout, dw, partial, N, D, H, W, st)
                 : b200_conv3d_wgrad_tc(x0, c0, x1, c1, dy, Cout, dw, partial, N, D, H, W, st);

@@ -13,6 +13,17 @@
 #include "tma_maps.cuh"
 #include <stdlib.h>
 
+// Build with `make EXTRA=-DB200_TC_DEBUG` for per-role cycle counters (env B200_TC_DEBUG=1 prints them) and for the
+// bottleneck knobs of env B200_TC3_SKIP (bit 0: no MMAs, 1: no epilogue global stores, 2: no epilogue TMEM loads,
+// 3: no TMA activation loads after the first ring fill).  The default build contains none of this.
+#ifdef B200_TC_DEBUG
+#define TC3_DBG(...) __VA_ARGS__
+#define TC3_CLOCK() clock64()
+#else
+#define TC3_DBG(...)
+#define TC3_CLOCK() 0ll
+#endif
+
 namespace {
 
 using bf16 = __nv_bfloat16;
@@ -37,7 +48,8 @@ struct Tc3Params {
   int wstationary;   // all slabs resident in shared memory (requires nchunks == 1)
   int wstages;       // streaming mode: ring depth (1 or 2)
   int total_tiles;
-  unsigned long long* dbg;  // optional per-CTA cycle counters (B200_TC_DEBUG): [cta][8]
+  unsigned long long* dbg;  // optional per-CTA cycle counters (B200_TC_DEBUG builds): [cta][8]
+  int skip;                 // B200_TC_DEBUG builds: bottleneck knobs (see top of file)
 };
 
 struct Tile { int tw, th, n, db, nchunk; };
@@ -105,12 +117,11 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
   tc::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // shuffle from a constant lane: provably warp-uniform (uniform registers)
 
-  if (warp == 0) {
+  if (warp == 0 TC3_DBG(&& !(p.skip & 128))) {
     // ===================== activation stages by TMA, continuous across tiles =====================
     {
       int it = 0;
-      long long dbg_prod_wait = 0;
-      const long long tstart = clock64();
+      TC3_DBG(long long dbg_prod_wait = 0; const long long tstart = clock64();)
       for (int k = 0; k < my_tiles; ++k) {
         const Tile t = decode_tile(p, blockIdx.x + k * gridDim.x);
         const int w0 = t.tw * 16, h0 = t.th * 16, d0 = t.db * p.dseg;
@@ -121,18 +132,24 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
           const int cc = c < p.c0 ? c : c - p.c0;
           for (int q = -1; q <= planes; ++q, ++it) {
             const int st = it % p.stages;
-            const long long t0 = clock64();
+            TC3_DBG(const long long t0 = clock64();)
             tc::mbar_wait(a_empty(st), ((it / p.stages) & 1) ^ 1);
-            dbg_prod_wait += clock64() - t0;
+            TC3_DBG(dbg_prod_wait += clock64() - t0;)
             if (tc::elect_one()) {
-              tc::mbar_arrive_expect_tx(a_full(st), kStageTx);
-              tma::load_5d(tc::smem_u32(act + st * kStageBytes), tm, cc, w0 - 1, h0 - 1, d0 + q, t.n, a_full(st));
+#ifdef B200_TC_DEBUG
+              if ((p.skip & 8) && it >= p.stages) tc::mbar_arrive(a_full(st));
+              else
+#endif
+              {
+                tc::mbar_arrive_expect_tx(a_full(st), kStageTx);
+                tma::load_5d(tc::smem_u32(act + st * kStageBytes), tm, cc, w0 - 1, h0 - 1, d0 + q, t.n, a_full(st));
+              }
             }
             __syncwarp();
           }
         }
       }
-      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 0] = dbg_prod_wait; p.dbg[blockIdx.x * 8 + 1] = clock64() - tstart; }
+      TC3_DBG(if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 0] = dbg_prod_wait; p.dbg[blockIdx.x * 8 + 1] = clock64() - tstart; })
     }
   } else if (warp == 1) {
     // ===================== weights =====================
@@ -167,18 +184,21 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
     const uint32_t wt_cols = (uint32_t)p.dseg * n_t;
     if (p.wstationary) { tc::mbar_wait(w_full(0), 0); tc::tc_fence_after(); }
     int it = 0, wi = 0;
-    long long dbg_wait_full = 0, dbg_wait_acc = 0;
-    const long long tstart = clock64();
+    TC3_DBG(long long dbg_wait_full = 0, dbg_wait_acc = 0; const long long tstart = clock64();)
     for (int k = 0; k < my_tiles; ++k) {
       const Tile t = decode_tile(p, blockIdx.x + k * gridDim.x);
       const int w0 = t.tw * 16, d0 = t.db * p.dseg;
       const int planes = min(p.dseg, p.D - d0);
+#ifdef B200_TC_DEBUG
+      const bool wt1_ = w0 + 8 < p.W;
+#else
       const bool wt1 = w0 + 8 < p.W;
+#endif
       const int set = k & 1;
       const uint32_t tset = tmem_base + (uint32_t)set * kSetCols;
-      const long long ta = clock64();
-      tc::mbar_wait(acc_empty(set), ((k >> 1) & 1) ^ 1);   // epilogue of tile k-2 has drained this set
-      dbg_wait_acc += clock64() - ta;
+      TC3_DBG(const long long ta = clock64();)
+      if (true TC3_DBG(&& !(p.skip & 512))) tc::mbar_wait(acc_empty(set), ((k >> 1) & 1) ^ 1);   // epilogue of tile k-2 has drained this set
+      TC3_DBG(dbg_wait_acc += clock64() - ta;)
       tc::tc_fence_after();
       for (int s = 0; s < p.slabs; ++s) {
         uint32_t w_lo;
@@ -194,14 +214,22 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
         }
         for (int q = -1; q <= planes; ++q, ++it) {
           const int st = it % p.stages;
-          const long long tf = clock64();
-          tc::mbar_wait(a_full(st), (it / p.stages) & 1);
-          dbg_wait_full += clock64() - tf;
+          TC3_DBG(const long long tf = clock64();)
+          if (true TC3_DBG(&& !(p.skip & 128))) tc::mbar_wait(a_full(st), (it / p.stages) & 1);
+          TC3_DBG(dbg_wait_full += clock64() - tf;)
           tc::tc_fence_after();
-          const uint32_t a_lo = a_lo0 + (tc::smem_u32(act + st * kStageBytes) >> 4);
+          uint32_t a_lo = a_lo0 + (tc::smem_u32(act + st * kStageBytes) >> 4);
+          TC3_DBG(if (p.skip & 32) a_lo = a_lo0 + (tc::smem_u32(act) >> 4);)
+          TC3_DBG(const bool wt1 = wt1_ && !(p.skip & 16);)
           const int kd_lo = max(0, q + 2 - planes), kd_hi = min(2, q + 1);
           const bool first = (s == 0 && kd_lo == 0);
           if (tc::elect_one()) {
+#ifdef B200_TC_DEBUG
+            if (p.skip & 1) {
+              tc::umma_commit(a_empty(st));
+              if (s == p.slabs - 1 && q >= 1) tc::umma_commit(acc_full(set, q - 1));
+            } else {
+#endif
             if (first) {
               // tap (0,0), kd = 0: the plane's very first contribution overwrites its accumulator
               const uint32_t col = tset + (uint32_t)(p.dseg - 2 - q) * n_t;
@@ -217,20 +245,26 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
             }
             for (int a = kd_lo; a <= kd_hi; a += p.kd_per_mma) {
               const int cnt = min(kd_hi, a + p.kd_per_mma - 1) - a + 1;
-              const uint32_t col = tset + (uint32_t)(p.dseg - 2 - q + a) * n_t;
+              uint32_t col = tset + (uint32_t)(p.dseg - 2 - q + a) * n_t;
+              TC3_DBG(if (p.skip & 256) col = tset;)
               const uint32_t idesc = idesc0 + idesc_step * (uint32_t)cnt;
               const uint32_t b_lo_g = w_lo + (uint32_t)a * n_t;
 #pragma unroll
               for (int tap = 0; tap < 9; ++tap) {
                 if (first && tap == 0) continue;
-                const uint32_t a_off = (uint32_t)(((tap / 3) * kHalo + (tap % 3)) * 32) >> 4;
-                const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo_g + (uint32_t)tap * b_tap16);
+                uint32_t a_off = (uint32_t)(((tap / 3) * kHalo + (tap % 3)) * 32) >> 4;
+                TC3_DBG(if (p.skip & 32) a_off = 0;)
+                uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo_g + (uint32_t)tap * b_tap16);
+                TC3_DBG(if (p.skip & 64) bd = ((uint64_t)b_hi << 32) | b_lo_g;)
                 tc::umma_bf16_ss(col, ((uint64_t)a_hi << 32) | (a_lo + a_off), bd, idesc, 1);
                 if (wt1) tc::umma_bf16_ss(col + wt_cols, ((uint64_t)a_hi << 32) | (a_lo + a_off + 16), bd, idesc, 1);
               }
             }
-            tc::umma_commit(a_empty(st));
-            if (s == p.slabs - 1 && q >= 1) tc::umma_commit(acc_full(set, q - 1));
+            if (true TC3_DBG(&& !(p.skip & 128))) tc::umma_commit(a_empty(st));
+            if (s == p.slabs - 1 && q >= 1 TC3_DBG(&& !(p.skip & 512))) tc::umma_commit(acc_full(set, q - 1));
+#ifdef B200_TC_DEBUG
+            }
+#endif
           }
           __syncwarp();
         }
@@ -240,15 +274,14 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
         }
       }
     }
-    if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 2] = dbg_wait_full; p.dbg[blockIdx.x * 8 + 3] = dbg_wait_acc; p.dbg[blockIdx.x * 8 + 4] = clock64() - tstart; }
-  } else if (warp >= 4) {
+    TC3_DBG(if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 2] = dbg_wait_full; p.dbg[blockIdx.x * 8 + 3] = dbg_wait_acc; p.dbg[blockIdx.x * 8 + 4] = clock64() - tstart; })
+  } else if (warp >= 4 TC3_DBG(&& !(p.skip & 512))) {
     // ===================== epilogue: warps 4-7 drain w-tile 0, warps 8-11 w-tile 1 =====================
     const int wt = (warp - 4) >> 2;
     const int ew = warp & 3;
     const int m = ew * 32 + lane;
     int bias_chunk = -1;
-    long long dbg_epi_wait = 0;
-    const long long tstart = clock64();
+    TC3_DBG(long long dbg_epi_wait = 0; const long long tstart = clock64();)
     uint32_t full_phase = 0;  // bit (set*8 + plane): parity of the next completion of that acc_full barrier (tiles may have < dseg planes)
     for (int k = 0; k < my_tiles; ++k) {
       const Tile t = decode_tile(p, blockIdx.x + k * gridDim.x);
@@ -268,11 +301,12 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
       const bool wt_ok = w0 + wt * 8 < p.W;
       const bool valid = h < p.H && w < p.W;
       for (int pl = 0; pl < planes; ++pl) {
-        const long long te = clock64();
+        TC3_DBG(const long long te = clock64();)
         tc::mbar_wait(acc_full(set, pl), (full_phase >> (set * 8 + pl)) & 1u);
-        dbg_epi_wait += clock64() - te;
+        TC3_DBG(dbg_epi_wait += clock64() - te;)
         full_phase ^= 1u << (set * 8 + pl);
         if (!wt_ok) continue;
+        TC3_DBG(if (p.skip & 4) continue;)
         tc::tc_fence_after();
         const int64_t row = (((int64_t)t.n * p.D + d0 + pl) * p.H + h) * p.W + w;
         const uint32_t col0 = (uint32_t)(set * kSetCols + (wt * p.dseg + (p.dseg - 1 - pl)) * p.n_tile);
@@ -288,7 +322,7 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
             __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(r[2 * i]) + bb.x, __uint_as_float(r[2 * i + 1]) + bb.y);
             packed[i] = *reinterpret_cast<uint32_t*>(&hb);
           }
-          if (valid) {
+          if (valid TC3_DBG(&& !(p.skip & 2))) {
             bf16* dst = ch < p.co0 ? p.y0 + row * p.co0 + ch : p.y1 + row * p.co1 + (ch - p.co0);
             reinterpret_cast<uint4*>(dst)[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             reinterpret_cast<uint4*>(dst)[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
@@ -300,7 +334,7 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(acc_empty(set));
     }
-    if (p.dbg && warp == 4 && lane == 0) { p.dbg[blockIdx.x * 8 + 5] = dbg_epi_wait; p.dbg[blockIdx.x * 8 + 6] = clock64() - tstart; }
+    TC3_DBG(if (p.dbg && warp == 4 && lane == 0) { p.dbg[blockIdx.x * 8 + 5] = dbg_epi_wait; p.dbg[blockIdx.x * 8 + 6] = clock64() - tstart; })
   }
 
   tc::tc_fence_before();
@@ -369,13 +403,18 @@ int b200_conv3d_k3_tc3(const void* x0, int c0, const void* x1, int c1, const voi
   }
   const int grid = p.total_tiles < B200_NUM_SMS ? p.total_tiles : B200_NUM_SMS;
   p.dbg = nullptr;
+  p.skip = 0;
+#ifdef B200_TC_DEBUG
   static unsigned long long* dbg_buf = nullptr;
   if (getenv("B200_TC_DEBUG")) {
     if (!dbg_buf) cudaMalloc(&dbg_buf, sizeof(unsigned long long) * 8 * B200_NUM_SMS);
     p.dbg = dbg_buf;
   }
+  { const char* e = getenv("B200_TC3_SKIP"); p.skip = e ? atoi(e) : 0; }
+#endif
   conv3d_tc3_kernel<<<grid, kThreads, smem, stream>>>(p, tm0, tm1);
   B200_CHECK_LAUNCH("conv3d_k3_tc3");
+#ifdef B200_TC_DEBUG
   if (p.dbg) {
     cudaStreamSynchronize(stream);
     static unsigned long long h[8 * B200_NUM_SMS];
@@ -385,5 +424,6 @@ int b200_conv3d_k3_tc3(const void* x0, int c0, const void* x1, int c1, const voi
     fprintf(stderr, "[tc3 dbg] per-CTA avg cycles: producer wait a_empty %.0f of %.0f | mma wait a_full %.0f, wait acc_empty %.0f of %.0f | epilogue(w4) wait acc_full %.0f of %.0f | tiles/CTA %.1f stages %d\n",
             a[0], a[1], a[2], a[3], a[4], a[5], a[6], (double)p.total_tiles / grid, p.stages);
   }
+#endif
   return B200_OK;
 }

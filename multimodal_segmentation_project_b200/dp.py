@@ -80,6 +80,10 @@ class FlatParams:
             p.grad = None
 
     def gather_grads(self, which="all", accumulate=False):
+        # A parameter that received no gradient this step gets a ZERO slice: FlatAdamW then still applies weight decay and
+        # decays its moments, whereas torch.optim.AdamW (the reference's optimiser) skips `grad is None` parameters.  Every
+        # parameter of UNet3D / the DANN variant receives a gradient on every step, so the two agree on the path this
+        # library covers; modules with conditionally unused parameters must not rely on the skip.
         lo, hi = {"all": (0, len(self.order)), "early": (0, self.n_early_params), "late": (self.n_early_params, len(self.order))}[which]
         dst, src = [], []
         for (n, p), v in zip(self.order[lo:hi], self._views[lo:hi]):
@@ -119,6 +123,8 @@ class DataParallelTrainer:
         self.autocast_dtype = autocast_dtype
         self.fp = FlatParams(model)
         dev = self.fp.flat.device
+        if self.world > 1:
+            self.broadcast_state(src=0)
         if optimizer_factory is not None:
             self.opt = optimizer_factory(self.fp)
         else:
@@ -146,6 +152,24 @@ class DataParallelTrainer:
         self.metrics = None
 
     # -- communication ---------------------------------------------------------------------------
+    def broadcast_state(self, src: int = 0):
+        """Every replica starts from rank `src`'s parameters and buffers — what DDP / Accelerate's prepare() does at
+        construction (train_unet.py:384-386); the reference seeds only when --seed is given, so ranks may have built
+        different initial weights.  One broadcast for the flat parameter buffer, one per dtype for the module buffers
+        (BatchNorm running_mean / running_var / num_batches_tracked)."""
+        dist.broadcast(self.fp.flat, src=src, group=self.pg)
+        by_dtype = {}
+        for b in self.model.buffers():
+            by_dtype.setdefault(b.dtype, []).append(b)
+        for dtype, bufs in by_dtype.items():
+            flat = torch.cat([b.detach().reshape(-1) for b in bufs])
+            dist.broadcast(flat, src=src, group=self.pg)
+            off = 0
+            with torch.no_grad():
+                for b in bufs:
+                    b.copy_(flat[off:off + b.numel()].view_as(b))
+                    off += b.numel()
+
     def _early_hook(self, _param):
         # called by autograd right after the sentinel's gradient was accumulated: everything in the
         # early bucket is final -> reduce it on the side stream while the encoder backward continues

@@ -243,6 +243,13 @@ class _ConvBNAct(torch.autograd.Function):
         N, D, H, W, _ = x0.shape
         Cout = weight.shape[0]
         dev = x0.device
+        # the statistics kernels write fp32 / int64 through raw pointers: anything else (model.half(), .to(bfloat16)) would
+        # overflow the buffers, so it is an error instead of a cast
+        for name, buf, want in (("running_mean", running_mean, torch.float32), ("running_var", running_var, torch.float32),
+                                ("num_batches_tracked", nbt, torch.int64)):
+            if buf is not None and (buf.dtype != want or not buf.is_contiguous() or not buf.is_cuda):
+                raise TypeError(f"BatchNorm3d.{name} must be a contiguous CUDA {want} tensor (got {buf.dtype} on {buf.device}): keep "
+                                "the module in float32 and select bf16 compute with torch.autocast or model.compute_dtype")
         impl = conv3d_select_impl(x0, x1, Cout, 0, impl)
         wpack = pack_conv3_weights(weight, pack_mode(impl, False), x0.dtype)
         conv_out, _ = conv3d_k3_raw(x0, x1, wpack, _f32(bias), Cout, 0, impl)
@@ -269,6 +276,7 @@ class _ConvBNAct(torch.autograd.Function):
         )
         ctx.save_for_backward(x0, x1, weight, conv_out, stats, dropmask)
         ctx.training = bool(training)
+        ctx.has_bias = bias is not None
         return y
 
     @staticmethod
@@ -310,6 +318,8 @@ class _ConvBNAct(torch.autograd.Function):
                 dw, db, keep = conv3d_wgrad_raw(x0, x1, dconv, want_bias=not ctx.training, side=side)
             if db is None:
                 db = torch.zeros(Cout, dtype=torch.float32, device=dev)
+            if not ctx.has_bias:
+                db = None
         dx0 = dx1 = None
         if need_x:
             c0 = x0.shape[-1]
@@ -323,9 +333,12 @@ class _ConvBNAct(torch.autograd.Function):
 
 
 def conv_bn_act(x0, x1, conv, bn, dropmask, training, impl=0):
+    if bn.momentum is None:
+        # torch switches to a cumulative moving average (factor 1 / num_batches_tracked) here; the reference never does
+        # (models/unet.py:12,16 use the default 0.1) and the fused finalize kernel takes a launch-constant factor
+        raise ValueError("BatchNorm3d(momentum=None) (cumulative moving average) is not supported by libb200unet")
     return _ConvBNAct.apply(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                            bn.num_batches_tracked, dropmask, training, bn.eps,
-                            0.1 if bn.momentum is None else bn.momentum, impl)
+                            bn.num_batches_tracked, dropmask, training, bn.eps, bn.momentum, impl)
 
 
 # --------------------------------------------------------------------------- MaxPool3d(2,2)
@@ -406,6 +419,7 @@ class _ConvT2(torch.autograd.Function):
         y = torch.empty((N, 2 * D, 2 * H, 2 * W, Cout), dtype=x.dtype, device=x.device)
         check(L.b200_convt2_fwd(_dt(x), _ptr(x), _ptr(w32), _ptr(b32), _ptr(y), N, D, H, W, Cin, Cout, _stream()), "convt2_fwd")
         ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
         return y
 
     @staticmethod
@@ -434,7 +448,7 @@ class _ConvT2(torch.autograd.Function):
             check(L.b200_convt2_bwd_data(_dt(x), _ptr(gy), _ptr(w32), _ptr(gx), N, D, H, W, Cin, Cout, _stream()), "convt2_bwd_data")
         join_side(side, x.device, x, gy, ws)
         del ws
-        return gx, dw, db
+        return gx, dw, (db if ctx.has_bias else None)
 
 
 def conv_transpose2(x, weight, bias):
@@ -488,6 +502,7 @@ class _FinalConv1x1(torch.autograd.Function):
         y = torch.empty((N, Cout, D, H, W), dtype=torch.float32, device=x.device)
         check(L.b200_conv1x1_fwd(_dt(x), _ptr(x), _ptr(w32), _ptr(b32), _ptr(y), N, S, Cin, Cout, int(round_bf16), _stream()), "conv1x1_fwd")
         ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
         return y
 
     @staticmethod
@@ -508,7 +523,7 @@ class _FinalConv1x1(torch.autograd.Function):
                                _stream()),
             "conv1x1_bwd",
         )
-        return gx, dw.reshape(weight.shape), db, None
+        return gx, dw.reshape(weight.shape), (db if ctx.has_bias else None), None
 
 
 def final_conv1x1(x, weight, bias, round_bf16=False):
@@ -606,6 +621,18 @@ class _SegLoss(torch.autograd.Function):
 def seg_loss(logits, target, mode, alpha=0.5, beta=0.5, teacher=None, kd_alpha=1.0, temperature=1.0):
     loss, _ = _SegLoss.apply(logits, target, teacher, mode, alpha, beta, kd_alpha, temperature)
     return loss
+
+
+def seg_loss_backward_raw(z, target, coef, gout, teacher=None, temperature=1.0):
+    """dlogits of the fused loss from explicit gradient coefficients (csrc/loss_kernels.cu coef layout); z fp32 contiguous."""
+    L = _lib.load()
+    N, C = z.shape[0], z.shape[1]
+    S = z.numel() // (N * C)
+    go = gout.detach().float().contiguous().reshape(1)
+    dz = torch.empty_like(z)
+    check(L.b200_seg_loss_bwd(_ptr(z), _ptr(teacher), _ptr(target.contiguous()), _ptr(coef), _ptr(go), float(temperature), N, C, S, _ptr(dz),
+                              _stream()), "seg_loss_bwd")
+    return dz
 
 
 def seg_loss_sums(logits, target):

@@ -12,8 +12,6 @@ Tversky epsilon 1e-6; ``combined_ce_tversky_loss`` hard-codes 0.3 / 0.7.
 """
 from __future__ import annotations
 
-import weakref
-
 import numpy as np
 import torch
 
@@ -53,21 +51,19 @@ def dice_only_loss(pred, target):
 
 
 # ------------------------------------------------------------------ multi-class metrics (reference :65-129)
-_conf_cache = {"pred": None, "target": None, "versions": None, "conf": None}
-
-
 def _confusion(pred, target):
-    # calculate_iou / calculate_dice / calculate_accuracy are called back to back on the same
-    # tensor objects (train_unet.py:229-232): compute the counts once.  The cache is keyed on object
-    # identity (weak references) + in-place version counters, never on addresses.
-    c = _conf_cache
-    if (c["pred"] is not None and c["pred"]() is pred and c["target"]() is target
-            and c["versions"] == (pred._version, target._version)):
-        return c["conf"]
-    conf = F.confusion_counts(pred, target).cpu().numpy()  # the reference syncs here too (`if sum > 0`)
-    c["pred"], c["target"] = weakref.ref(pred), weakref.ref(target)
-    c["versions"], c["conf"] = (pred._version, target._version), conf
-    return conf
+    # One argmax + confusion-count pass per call.  There is deliberately NO cache across calls: libb200unet kernels and
+    # CUDA-graph replays rewrite tensors through raw pointers without bumping torch's version counters, so any key built
+    # from tensor identity would serve stale counts.  Callers that want all three metrics from one pass use
+    # dice_iou_accuracy() below.
+    return F.confusion_counts(pred, target).cpu().numpy()  # the reference syncs here too (`if sum > 0`)
+
+
+def dice_iou_accuracy(pred, target):
+    """(calculate_dice, calculate_iou, calculate_accuracy) of the reference (utils/metrics.py:65-129) from ONE pass over
+    the logits; each value is bit-identical to the corresponding single call."""
+    conf = _confusion(pred, target)
+    return _dice_from(conf, pred), _iou_from(conf, pred), _accuracy_from(conf, pred, target)
 
 
 def dice_iou_from_confusion(conf: np.ndarray, first_spatial: int):
@@ -92,30 +88,39 @@ def _first_spatial(pred):
     return pred.shape[2] if pred.dim() > 2 else 1
 
 
-def calculate_iou(pred, target):
-    """reference utils/metrics.py:65-90."""
-    conf = _confusion(pred, target)
+def _iou_from(conf, pred):
     _, iou, valid = dice_iou_from_confusion(conf, _first_spatial(pred))
     if valid == 0:
         return 0 / max(valid, 1)
     return torch.tensor(_f32(iou / _f32(valid)), dtype=torch.float32, device=pred.device)
 
 
-def calculate_dice(pred, target):
-    """reference utils/metrics.py:92-117."""
-    conf = _confusion(pred, target)
+def _dice_from(conf, pred):
     dice, _, valid = dice_iou_from_confusion(conf, _first_spatial(pred))
     if valid == 0:
         return 0 / max(valid, 1)
     return torch.tensor(_f32(dice / _f32(valid)), dtype=torch.float32, device=pred.device)
 
 
-def calculate_accuracy(pred, target):
-    """reference utils/metrics.py:119-129: (argmax == target).float().mean()."""
-    conf = _confusion(pred, target)
+def _accuracy_from(conf, pred, target):
     n = int(target.numel())
     correct = int(np.trace(conf))
     return torch.tensor(_f32(_f32(correct) / _f32(n)), dtype=torch.float32, device=pred.device)
+
+
+def calculate_iou(pred, target):
+    """reference utils/metrics.py:65-90."""
+    return _iou_from(_confusion(pred, target), pred)
+
+
+def calculate_dice(pred, target):
+    """reference utils/metrics.py:92-117."""
+    return _dice_from(_confusion(pred, target), pred)
+
+
+def calculate_accuracy(pred, target):
+    """reference utils/metrics.py:119-129: (argmax == target).float().mean()."""
+    return _accuracy_from(_confusion(pred, target), pred, target)
 
 
 def per_class_dice_iou(pred, target, classes=(1, 2, 3)):
@@ -194,15 +199,25 @@ def dice_loss(pred, target, epsilon=1e-6):
 
 
 class _BinaryDice(torch.autograd.Function):
+    """1 - (2 I + eps) / (P + T + eps) over the class-1 plane of softmax([0, x]) == sigmoid(x)."""
+
     @staticmethod
     def forward(ctx, planes, tgt, eps):
-        sums = F.seg_loss_sums(planes, tgt)  # [CE, KL, -, -, (I,P,T,-) per class]
+        z = planes.detach().float().contiguous()
+        sums = F.seg_loss_sums(z, tgt)  # [CE, KL, -, -, (I,P,T,-) per class] float64
         I, P, T = sums[8], sums[9], sums[10]
-        dice = (2.0 * I + eps) / (P + T + eps)
-        ctx.save_for_backward(planes, tgt, sums)
-        ctx.eps = eps
-        return (1.0 - dice).float()
+        num, den = 2.0 * I + eps, P + T + eps
+        # gradient coefficients in the layout seg_loss_bwd reads (csrc/loss_kernels.cu: [w_ce/N, kd, a_c..., b_c...]):
+        # dL/dp_1(v) = a_1 * t(v) + b_1 with a_1 = -2/den, b_1 = num/den^2; no CE / KD term, nothing for class 0
+        coef = torch.zeros(2 + 2 * 2, dtype=torch.float32, device=z.device)
+        coef[3] = (-2.0 / den).float()
+        coef[5] = (num / (den * den)).float()
+        ctx.save_for_backward(z, tgt, coef)
+        ctx.in_dtype = planes.dtype
+        return (1.0 - num / den).float()
 
     @staticmethod
     def backward(ctx, g):
-        raise NotImplementedError("dice_loss backward: the reference never trains with this loss; use combined_loss")
+        z, tgt, coef = ctx.saved_tensors
+        dz = F.seg_loss_backward_raw(z, tgt, coef, g)
+        return dz.to(ctx.in_dtype), None, None

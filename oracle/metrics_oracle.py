@@ -96,3 +96,39 @@ def dice_iou_accuracy(pred, target):
     if valid == 0:
         return 0, 0, acc
     return f32(dice / f32(valid)), f32(iou / f32(valid)), acc
+
+
+# ---- binary helpers (dead code in the reference's scripts, part of the module API) -----------
+def binary_counts(pred, target):
+    """Per-sample integer counts behind utils/metrics.py:42-63: I = #(pred>0.5 & t), P = #(pred>0.5), T = sum(t), correct."""
+    B = pred.shape[0]
+    p = (pred.reshape(B, -1) > 0.5).cpu().numpy()
+    t = target.reshape(B, -1).cpu().numpy() != 0
+    return [(int((p[b] & t[b]).sum()), int(p[b].sum()), int(t[b].sum()), int((p[b] == t[b]).sum())) for b in range(B)]
+
+
+def dice_score(pred, target, epsilon=1e-6):
+    """utils/metrics.py:42-48 — fp32 per-sample ratios, then their fp32 mean"""
+    f32 = np.float32
+    v = [f32(f32(f32(2.0) * f32(I)) + f32(epsilon)) / f32(f32(f32(P) + f32(T)) + f32(epsilon)) for I, P, T, _ in binary_counts(pred, target)]
+    return float(np.mean(np.asarray(v, dtype=np.float32), dtype=np.float32))
+
+
+def iou_score(pred, target, epsilon=1e-6):
+    """utils/metrics.py:50-56"""
+    f32 = np.float32
+    v = [f32(f32(I) + f32(epsilon)) / f32(f32(f32(f32(P) + f32(T)) - f32(I)) + f32(epsilon)) for I, P, T, _ in binary_counts(pred, target)]
+    return float(np.mean(np.asarray(v, dtype=np.float32), dtype=np.float32))
+
+
+def accuracy_score(pred, target):
+    """utils/metrics.py:58-63"""
+    f32 = np.float32
+    return float(f32(sum(c[3] for c in binary_counts(pred, target))) / f32(target.numel()))
+
+
+def dice_loss(pred, target, epsilon=1e-6):
+    """utils/metrics.py:6-12: 1 - (2 sum(sigmoid(x) t) + eps) / (sum(sigmoid(x)) + sum(t) + eps)"""
+    p = torch.sigmoid(pred).reshape(-1)
+    t = target.reshape(-1).to(p.dtype)
+    return 1 - (2.0 * (p * t).sum() + epsilon) / (p.sum() + t.sum() + epsilon)

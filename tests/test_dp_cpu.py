@@ -155,3 +155,50 @@ def test_gradient_accumulation_two_ranks_gloo():
                 (_loss(model(x), y) / 4).backward()
         opt.step(1.0)
     assert torch.allclose(fp.flat, out[0], rtol=1e-5, atol=1e-7)
+
+
+class _TinyBN(_Tiny):
+    def __init__(self):
+        super().__init__()
+        self.norm = torch.nn.BatchNorm3d(4)
+
+    def forward(self, x):
+        for e in self.encoder:
+            x = torch.relu(e(x))
+        return self.final_conv(torch.relu(self.norm(self.bottleneck(x))))
+
+
+def _unseeded_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(1234 + 77 * rank)              # the reference seeds only with --seed: ranks build DIFFERENT models
+    model = _TinyBN()
+    with torch.no_grad():
+        model.norm.running_mean.fill_(float(rank + 1))
+        model.norm.num_batches_tracked.fill_(5 * (rank + 1))
+    init = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()
+    tr = DataParallelTrainer(model, _loss, autocast_dtype=None, optimizer_factory=lambda fp: _TorchFlatAdamW(fp))
+    after_ctor = tr.fp.flat.detach().clone()
+    bufs = (model.norm.running_mean.clone(), model.norm.num_batches_tracked.clone())
+    g = torch.Generator().manual_seed(100 + rank)
+    tr.step(torch.randn(2, 1, 6, 6, 6, generator=g), torch.randint(0, 3, (2, 1, 6, 6, 6), generator=g))
+    out[rank] = (init, after_ctor, bufs, tr.fp.flat.detach().clone())
+    dist.destroy_process_group()
+
+
+def test_constructor_broadcasts_rank0_state():
+    """DDP / Accelerate.prepare broadcast rank 0's parameters and buffers at construction (train_unet.py:384-386); without it
+    unseeded ranks would train permanently different replicas."""
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_unseeded_worker, args=(2, port, out), nprocs=2, join=True)
+    init0, ctor0, bufs0, step0 = out[0]
+    init1, ctor1, bufs1, step1 = out[1]
+    assert not torch.equal(init0, init1), "the test needs ranks that start from different weights"
+    n = init0.numel()
+    # FlatParams orders early-bucket parameters first, so compare as multisets through sorting
+    assert torch.equal(ctor0, ctor1) and torch.equal(torch.sort(ctor0[:n]).values, torch.sort(init0).values)
+    assert torch.equal(bufs0[0], bufs1[0]) and float(bufs1[0][0]) == 1.0
+    assert int(bufs0[1]) == int(bufs1[1]) == 5
+    assert torch.equal(step0, step1), "replicas diverged after one step"

@@ -1,0 +1,358 @@
+"""GPU: parity AT THE CONFIGURATIONS BASELINE.json names (round-1 verdict item 1).
+
+cfg 2  2 x 128^3 bf16 train step        vs the oracle under CUDA bf16 autocast (train_unet.py:222-225)
+cfg 3  distillation step, 128^3 bf16    vs the oracle (distill_unet.py:107-119)
+cfg 4  DANN step, 128^3 bf16            vs the oracle (train_dann.py:243-260)
+cfg 5  512 x 512 x 256 sliding window   vs the oracle loop over windows + the evaluator's metric rules (test_model.py:248-285)
+(e)    2-GPU NCCL data-parallel step    vs the single-process averaged-gradient update (train_unet.py:221-226)
+
+The oracle runs on the GPU through torch ops (cuDNN) only as the checker.  Tolerances are north_star's: rel-L2 <= 1e-2 for
+bf16 logits / loss / gradients, <= 1e-4 fp32; argmax masks and confusion counts bit-exact on identical logits.  Every
+measured distance is appended to $B200_PARITY_LOG (default gpurun_out/parity_r02.jsonl) so that the numbers behind the
+assertions can be committed under profiles/.
+"""
+import functools
+import json
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from multimodal_segmentation_project_b200 import functional as F
+from multimodal_segmentation_project_b200.dp import DataParallelTrainer
+from multimodal_segmentation_project_b200.inference import evaluate_volume, organ_metrics_from_confusion, window_starts
+from multimodal_segmentation_project_b200.models.unet import UNet3D
+from multimodal_segmentation_project_b200.models.unet_dann import UNet3D as UNet3DDann
+from multimodal_segmentation_project_b200.synthetic import structured_volume
+from multimodal_segmentation_project_b200.train_dann import DomainDiscriminator, domain_cross_entropy, grad_reverse
+from multimodal_segmentation_project_b200.utils import metrics as M
+from oracle import dann_oracle as OD
+from oracle import metrics_oracle as OM
+from oracle.unet_oracle import clone_for_autograd, init_state_dict, train_step_grads, trainable, unet3d_forward
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BF16_TOL = 1e-2     # north_star: rel. L2 <= 1e-2 bf16
+FP32_TOL = 1e-4     # north_star: rel. L2 <= 1e-4 fp32
+
+
+def _log(**rec):
+    path = os.environ.get("B200_PARITY_LOG", os.path.join(ROOT, "gpurun_out", "parity_r02.jsonl"))
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "a") as f:
+            f.write(json.dumps(rec) + "\n")
+    except OSError:
+        pass
+    print(json.dumps(rec))
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _skip_bias(k):  # conv biases feeding a train-mode BatchNorm: analytically zero gradient (round-off noise in both)
+    return k.endswith("double_conv.0.bias") or k.endswith("double_conv.4.bias")
+
+
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@functools.lru_cache(maxsize=None)
+def _warm_weights(seed, steps=12, size=64):
+    """A few fp32 AdamW steps of the ORACLE at a reduced size (the bf16 protocol is calibrated on weights
+    that have left the initialisation point); returns a CPU state_dict."""
+    sd = init_state_dict(1, 4, seed=seed)
+    x, y = structured_volume(2, size, seed=900 + seed)
+    p = {k: v.clone().cuda() for k, v in sd.items()}
+    names = trainable(sd)
+    for k in names:
+        p[k].requires_grad_(True)
+    opt = torch.optim.AdamW([p[k] for k in names], lr=1e-3)
+    xc, yc = x.cuda(), y.cuda()
+    for _ in range(steps):
+        opt.zero_grad()
+        OM.combined_loss(unet3d_forward(p, xc, True), yc).backward()
+        opt.step()
+    return {k: v.detach().cpu() for k, v in p.items()}
+
+
+def _net(sd, cls=UNet3D):
+    net = cls(1, 4, dropout_rate=0.0).cuda()
+    net.load_state_dict(sd)
+    return net
+
+
+def _grads(named, ref, keys):
+    ours = torch.cat([named[k].grad.flatten().float() for k in keys])
+    theirs = torch.cat([ref[k].flatten().float().to(ours.device) for k in keys])
+    return ours, theirs
+
+
+# ------------------------------------------------------------------------------------------------ cfg 2
+def test_cfg2_train_step_2x128_bf16_vs_autocast_oracle(cuda_dev):
+    """The step every headline number is measured on: 2 x 128^3, bf16 autocast, Dice+CE, forward + backward."""
+    _no_tf32()
+    sd = _warm_weights(0)
+    x, y = structured_volume(2, 128, seed=1234)
+    xc, yc = x.cuda(), y.cuda()
+    l16, z16, g16, buf16 = train_step_grads(sd, xc, yc, OM.combined_loss, autocast_dtype=torch.bfloat16)
+    l32, z32, g32, _ = train_step_grads(sd, xc, yc, OM.combined_loss)
+    net = _net(sd).train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = net(xc)
+    loss = M.combined_loss(logits.float(), yc)
+    loss.backward()
+    keys = [k for k in g16 if not _skip_bias(k)]
+    ours, r16 = _grads(dict(net.named_parameters()), g16, keys)
+    _, r32 = _grads(dict(net.named_parameters()), g32, keys)
+    rec = dict(test="cfg2_train_step_2x128_bf16", logits_vs_bf16_oracle=rel_l2(logits, z16), logits_vs_fp32_oracle=rel_l2(logits, z32),
+               oracle_bf16_vs_fp32_logits=rel_l2(z16, z32), grads_vs_bf16_oracle=rel_l2(ours, r16), grads_vs_fp32_oracle=rel_l2(ours, r32),
+               oracle_bf16_vs_fp32_grads=rel_l2(r16, r32), loss=loss.item(), loss_bf16_oracle=l16.item(), loss_fp32_oracle=l32.item(),
+               argmax_agreement=(logits.argmax(1) == z16.argmax(1)).float().mean().item())
+    _log(**rec)
+    # north_star tolerance, each quantity by name (no either-or)
+    assert rec["logits_vs_bf16_oracle"] <= BF16_TOL, rec
+    assert abs(loss.item() - l16.item()) <= BF16_TOL * abs(l16.item()), rec
+    assert rec["grads_vs_bf16_oracle"] <= BF16_TOL, rec
+    # and no further from the fp32 truth than the reference's own bf16 path is (App. F protocol), by name as well
+    assert rec["logits_vs_fp32_oracle"] <= 1.25 * rec["oracle_bf16_vs_fp32_logits"] + 1e-3, rec
+    assert rec["grads_vs_fp32_oracle"] <= 1.25 * rec["oracle_bf16_vs_fp32_grads"] + 1e-3, rec
+    assert rec["argmax_agreement"] >= 0.995, rec
+    # metrics on IDENTICAL logits: bit-exact counts and scalars (Appendix E)
+    conf = F.confusion_counts(logits, yc).cpu().numpy()
+    assert np.array_equal(conf, OM.confusion_counts(logits.float().cpu(), y))
+    d, i, a = OM.dice_iou_accuracy(logits.float().cpu(), y)
+    md, mi, ma = M.dice_iou_accuracy(logits, yc)
+    assert float(md) == float(d) and float(mi) == float(i) and float(ma) == float(a)
+    # running statistics follow the batch statistics of the bf16 activations
+    sdn = net.state_dict()
+    for k in ("encoder.0.double_conv.1.running_mean", "decoder.3.double_conv.5.running_var", "bottleneck.double_conv.1.running_var"):
+        assert rel_l2(sdn[k], buf16[k]) <= BF16_TOL, k
+
+
+def test_cfg2_graph_step_loss_matches_oracle(cuda_dev):
+    """bench.py's timed object: the graph-captured DataParallelTrainer step at 2 x 128^3 — first loss and the loss after a
+    few optimiser steps follow the oracle's bf16 training trajectory (torch AdamW on the oracle's autocast gradients)."""
+    _no_tf32()
+    sd = init_state_dict(1, 4, seed=0)
+    x, y = structured_volume(2, 128, seed=1234)
+    xc, yc = x.cuda(), y.cuda()
+    p = {k: v.clone().cuda() for k, v in sd.items()}
+    names = trainable(sd)
+    for k in names:
+        p[k].requires_grad_(True)
+    opt = torch.optim.AdamW([p[k] for k in names], lr=1e-3, weight_decay=1e-2)
+    ref_losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            z = unet3d_forward(p, xc, True)
+        l = OM.combined_loss(z.float(), yc)
+        l.backward()
+        opt.step()
+        ref_losses.append(l.item())
+    net = _net(sd).train()
+    tr = DataParallelTrainer(net, M.combined_loss, lr=1e-3, weight_decay=1e-2, autocast_dtype=torch.bfloat16)
+    flat0 = tr.fp.flat.clone()
+    tr.capture(xc, yc, warmup=3)             # warm-up steps move the weights: restore the starting point afterwards
+    tr.fp.flat.copy_(flat0)
+    tr.opt.m.zero_(); tr.opt.v.zero_(); tr.opt.step_count.zero_()
+    ours = [tr.replay().item() for _ in range(3)]
+    _log(test="cfg2_graph_step_losses", ours=ours, oracle=ref_losses)
+    assert abs(ours[0] - ref_losses[0]) <= BF16_TOL * abs(ref_losses[0])
+    for a, b in zip(ours[1:], ref_losses[1:]):
+        assert abs(a - b) <= 3e-2 * abs(b), (ours, ref_losses)   # Adam's sign-like first steps amplify bf16 differences
+
+
+# ------------------------------------------------------------------------------------------------ cfg 3
+def test_cfg3_distillation_step_128_bf16(cuda_dev):
+    """frozen teacher (eval) + student (train), distillation_loss(alpha=.7, T=2), 1 x 128^3... the reference's batch is 2."""
+    _no_tf32()
+    sd_s, sd_t = _warm_weights(0), _warm_weights(1)
+    x, y = structured_volume(2, 128, seed=11)
+    xc, yc = x.cuda(), y.cuda()
+    p = clone_for_autograd(sd_s, "cuda")
+    pt = {k: v.clone().cuda() for k, v in sd_t.items()}
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        t_ref = unet3d_forward(pt, xc, training=False)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        s_ref = unet3d_forward(p, xc, training=True)
+    ref_loss = OM.distillation_loss(s_ref.float(), t_ref.float(), yc, 0.7, 2.0)
+    ref_loss.backward()
+    student, teacher = _net(sd_s).train(), _net(sd_t).eval()
+    for q in teacher.parameters():
+        q.requires_grad = False
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        sl = student(xc)
+        with torch.no_grad():
+            tl = teacher(xc)
+    loss = M.distillation_loss(sl.float(), tl.float(), yc, alpha=0.7, temperature=2.0)
+    loss.backward()
+    keys = [k for k in trainable(sd_s) if not _skip_bias(k)]
+    ours, ref_g = _grads(dict(student.named_parameters()), {k: p[k].grad for k in keys}, keys)
+    rec = dict(test="cfg3_distillation_128_bf16", teacher_logits=rel_l2(tl, t_ref), student_logits=rel_l2(sl, s_ref), grads=rel_l2(ours, ref_g),
+               loss=loss.item(), loss_oracle=ref_loss.item())
+    _log(**rec)
+    assert rec["teacher_logits"] <= BF16_TOL and rec["student_logits"] <= BF16_TOL, rec
+    assert abs(loss.item() - ref_loss.item()) <= BF16_TOL * abs(ref_loss.item()), rec
+    assert rec["grads"] <= BF16_TOL, rec
+    assert all(q.grad is None for q in teacher.parameters())
+
+
+# ------------------------------------------------------------------------------------------------ cfg 4
+def test_cfg4_dann_step_128_bf16(cuda_dev):
+    """source + target forwards, task loss on source, domain CE through gradient reversal, total = task + lambda * domain
+    (lambda applied twice) at 2 x 128^3 per domain, bf16."""
+    _no_tf32()
+    lam = 0.3
+    sd = _warm_weights(0)
+    dsd = OD.init_discriminator(256, seed=5)
+    xs, ys = structured_volume(2, 128, seed=21)
+    xt, _ = structured_volume(2, 128, seed=22)
+    xs, ys, xt = xs.cuda(), ys.cuda(), xt.cuda()
+    p = clone_for_autograd(sd, "cuda")
+    d_ = {k: v.clone().cuda().requires_grad_(True) for k, v in dsd.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        so, sf = unet3d_forward(p, xs, True, return_features=True)
+        _, tf = unet3d_forward(p, xt, True, return_features=True)
+    task = OM.combined_ce_tversky_loss(so.float(), ys, 0.5, 0.5)
+    dom = OD.domain_loss(d_, sf.float(), tf.float(), lam)
+    (task + lam * dom).backward()
+    seg = _net(sd, UNet3DDann).train()
+    disc = DomainDiscriminator(256).cuda()
+    disc.load_state_dict(dsd)
+    disc.eval()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        o_s, f_s = seg(xs, return_features=True)
+        _, f_t = seg(xt, return_features=True)
+    task_c = M.combined_ce_tversky_loss(o_s.float(), ys, alpha=0.5, beta=0.5)
+    labels = torch.cat([torch.zeros(2, dtype=torch.long), torch.ones(2, dtype=torch.long)]).cuda()
+    dom_c = domain_cross_entropy(torch.cat([disc(grad_reverse(f_s.float(), lam)), disc(grad_reverse(f_t.float(), lam))], dim=0), labels)
+    (task_c + lam * dom_c).backward()
+    keys = [k for k in trainable(sd) if not _skip_bias(k)]
+    ours, ref_g = _grads(dict(seg.named_parameters()), {k: p[k].grad for k in keys}, keys)
+    dg = rel_l2(torch.cat([q.grad.flatten() for _, q in disc.named_parameters()]), torch.cat([d_[k].grad.flatten() for k, _ in disc.named_parameters()]))
+    rec = dict(test="cfg4_dann_128_bf16", source_logits=rel_l2(o_s, so), features=rel_l2(f_s, sf), task=task_c.item(), task_oracle=task.item(),
+               domain=dom_c.item(), domain_oracle=dom.item(), seg_grads=rel_l2(ours, ref_g), disc_grads=dg)
+    _log(**rec)
+    assert rec["source_logits"] <= BF16_TOL and rec["features"] <= BF16_TOL, rec
+    assert abs(task_c.item() - task.item()) <= BF16_TOL * abs(task.item()), rec
+    assert abs(dom_c.item() - dom.item()) <= BF16_TOL * abs(dom.item()), rec
+    assert rec["seg_grads"] <= BF16_TOL and rec["disc_grads"] <= BF16_TOL, rec
+    assert int(seg.state_dict()["decoder.3.double_conv.5.num_batches_tracked"]) == 2
+
+
+# ------------------------------------------------------------------------------------------------ cfg 5
+def test_cfg5_sliding_window_512x512x256(cuda_dev):
+    """CT-sized volume, 128^3 windows at stride 128 (32 windows), fp32: stitched logits vs the oracle's window loop, argmax
+    masks / confusion counts bit-exact on identical logits, per-organ Dice/IoU by the evaluator's rule."""
+    _no_tf32()
+    sd = _warm_weights(0, steps=6)
+    D, H, W = 256, 512, 512
+    vol, lab = structured_volume(1, (D, H, W), seed=31)
+    volc, labc = vol.cuda(), lab.cuda()
+    win = stride = 128
+    net = _net(sd).train()
+    logits, conf, organs = evaluate_volume(net, volc, labc, window=win, stride=stride)
+    assert net.training and tuple(logits.shape) == (1, 4, D, H, W)
+    # oracle loop (test_model.py:248 applied per window, eval mode), accumulated on the GPU in fp32
+    pg = {k: v.cuda() for k, v in sd.items()}
+    acc = torch.zeros(1, 4, D, H, W, device="cuda")
+    cnt = torch.zeros(D, H, W, device="cuda")
+    with torch.no_grad():
+        for d0 in window_starts(D, win, stride):
+            for h0 in window_starts(H, win, stride):
+                for w0 in window_starts(W, win, stride):
+                    out = unet3d_forward(pg, volc[:, :, d0:d0 + win, h0:h0 + win, w0:w0 + win], training=False)
+                    acc[:, :, d0:d0 + win, h0:h0 + win, w0:w0 + win] += out
+                    cnt[d0:d0 + win, h0:h0 + win, w0:w0 + win] += 1
+    ref = acc / cnt
+    del acc, cnt
+    err = rel_l2(logits, ref)
+    agree = (logits.argmax(1) == ref.argmax(1)).float().mean().item()
+    ref_conf = OM.confusion_counts(logits.cpu(), lab)          # numpy bincount over 67 M voxels on the SAME logits
+    _log(test="cfg5_sliding_window_512x512x256", logits_vs_oracle=err, argmax_agreement=agree, voxels=int(lab.numel()), conf_trace=int(np.trace(conf)))
+    assert err <= FP32_TOL
+    assert agree >= 0.9999
+    assert np.array_equal(conf, ref_conf) and int(conf.sum()) == D * H * W
+    assert torch.equal(F.argmax_mask(logits).cpu().long(), logits.argmax(1).cpu())
+    assert organs == organ_metrics_from_confusion(ref_conf)
+    # and the counts of the oracle's own stitched logits differ only where its argmax differs
+    oc = OM.confusion_counts(ref.cpu(), lab)
+    assert np.abs(oc - conf).sum() <= 2 * round((1 - agree) * D * H * W) + 2
+
+
+# ------------------------------------------------------------------------------------------------ (e) 2-GPU NCCL
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _nccl_worker(rank, world, port, size, steps, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    sd = init_state_dict(1, 4, seed=100 + rank)                  # ranks start DIFFERENT: the constructor must broadcast rank 0's
+    net = UNet3D(1, 4, dropout_rate=0.0).cuda()
+    net.load_state_dict(sd)
+    net.train()
+    x, y = structured_volume(2, size, seed=500 + rank)
+    xc, yc = x.cuda(), y.cuda()
+    tr = DataParallelTrainer(net, M.combined_loss, lr=1e-3, weight_decay=1e-2, autocast_dtype=torch.bfloat16)
+    start = tr.fp.flat.clone()
+    tr.capture(xc, yc, warmup=3)
+    tr.fp.flat.copy_(start)
+    tr.opt.m.zero_(); tr.opt.v.zero_(); tr.opt.step_count.zero_()
+    for _ in range(steps):
+        tr.replay()
+    torch.cuda.synchronize()
+    torch.save({"flat": tr.fp.flat.cpu(), "start": start.cpu(), "order": [n for n, _ in tr.fp.order]}, os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("size", [32, 64])
+def test_two_gpu_nccl_graph_step_matches_single_process_average(cuda_dev, tmp_path, size):
+    """After K graph replays (early bucket all-reduced on the side stream inside the captured graph) every rank holds
+    bit-identical parameters, and they equal the single-process update with the MEAN of the per-rank gradients."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under `gpurun --gpus 2`)")
+    import torch.multiprocessing as mp
+    steps = 3
+    mp.spawn(_nccl_worker, args=(2, _free_port(), size, steps, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "rank0.pt"), torch.load(tmp_path / "rank1.pt")
+    assert torch.equal(r0["start"], r1["start"]), "constructor did not broadcast rank 0's parameters"
+    assert torch.equal(r0["flat"], r1["flat"]), "ranks diverged"
+    # single process, same kernels: per-rank gradients computed one after the other, summed, AdamW with grad / 2
+    sd = init_state_dict(1, 4, seed=100)
+    net = UNet3D(1, 4, dropout_rate=0.0).cuda()
+    net.load_state_dict(sd)
+    net.train()
+    tr = DataParallelTrainer(net, M.combined_loss, lr=1e-3, weight_decay=1e-2, autocast_dtype=torch.bfloat16)
+    assert [n for n, _ in tr.fp.order] == r0["order"]
+    assert torch.equal(tr.fp.flat.cpu(), r0["start"])
+    data = [tuple(t.cuda() for t in structured_volume(2, size, seed=500 + r)) for r in range(2)]
+    for _ in range(steps):
+        total = torch.zeros_like(tr.fp.grad)
+        for xc, yc in data:
+            tr.fp.detach_grads()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = net(xc)
+            M.combined_loss(out.float(), yc).backward()
+            F.join_pending()
+            tr.fp.gather_grads("all")
+            total += tr.fp.grad
+        tr.fp.grad.copy_(total)
+        tr.opt.step(grad_scale=0.5)
+    a, b = tr.fp.flat.cpu(), r0["flat"]
+    same = (a == b).float().mean().item()
+    _log(test=f"two_gpu_nccl_{size}", bit_identical_fraction=same, rel_l2=rel_l2(a, b), max_abs=(a - b).abs().max().item())
+    # a 2-rank sum is one commutative fp32 addition per element and every kernel is run-to-run deterministic: bit-exact
+    assert torch.equal(a, b), (same, rel_l2(a, b))

@@ -668,3 +668,64 @@ def test_conv3d_wgrad_tcgen05_vs_oracle(cuda_dev, case):
     # bf16-exact inputs, fp32 accumulation in TMEM, fp64 fixed-order split-K reduction
     assert rel_l2(dw, w.grad) <= 2e-5
     assert rel_l2(db, gy.double().sum(dim=(0, 2, 3, 4))) <= 2e-5
+
+
+# ----------------------------------------------------------------------------- binary helpers (a13)
+BINARY_CASES = ["a", "b", "c", "empty_target", "full_target"]
+
+
+@pytest.mark.parametrize("case", BINARY_CASES)
+def test_binary_helpers_vs_reference_golden(cuda_dev, golden_dir, case):
+    """utils/metrics.py:6-12 (dice_loss, incl. its gradient), :42-63 (dice_score / iou_score / accuracy_score),
+    :131-135 (calculate_metrics) against the unmodified reference (oracle/make_golden_binary.py)."""
+    g = _load(golden_dir, "binary_helpers.npz")
+    prob, tgt = torch.from_numpy(g[f"{case}/prob"]).cuda(), torch.from_numpy(g[f"{case}/target"]).cuda()
+    # integer counts -> fp32 ratios in the reference's order: bit-exact
+    assert M.dice_score(prob, tgt) == float(g[f"{case}/dice_score"])
+    assert M.iou_score(prob, tgt) == float(g[f"{case}/iou_score"])
+    assert M.accuracy_score(prob, tgt) == float(g[f"{case}/accuracy_score"])
+    assert list(M.calculate_metrics(prob, tgt)) == [float(v) for v in g[f"{case}/calculate_metrics"]]
+    z = torch.from_numpy(g[f"{case}/logits"]).cuda().requires_grad_(True)
+    loss = M.dice_loss(z, tgt)
+    loss.backward()
+    assert abs(loss.item() - float(g[f"{case}/dice_loss"])) <= 1e-5 * max(1.0, abs(float(g[f"{case}/dice_loss"])))
+    ref = torch.from_numpy(g[f"{case}/dice_loss_grad"])
+    assert z.grad is not None and z.grad.shape == z.shape
+    assert (z.grad.cpu() - ref).abs().max().item() <= 1e-5 * max(float(ref.abs().max()), 1e-12) + 1e-9
+
+
+def test_wgrad_kernel_failure_surfaces_as_error(cuda_dev):
+    """A failing weight-gradient kernel selection must raise, never hand AdamW an uninitialised dw (round-1 advisor finding)."""
+    x = torch.randn(1, 8, 16, 16, 32, device="cuda").to(torch.bfloat16)
+    dy = torch.randn(1, 8, 16, 16, 32, device="cuda").to(torch.bfloat16)
+    dw, _ = F.conv3d_wgrad_raw(x, None, dy, want_bias=False)      # the wide-row tcgen05 path serves this shape
+    _lib.check(_lib.load().b200_debug_fail_next_wgrad(1), "debug_fail_next_wgrad")
+    try:
+        with pytest.raises(ValueError, match="injected failure"):
+            F.conv3d_wgrad_raw(x, None, dy, want_bias=False)
+    finally:
+        _lib.load().b200_debug_fail_next_wgrad(0)
+    dw2, _ = F.conv3d_wgrad_raw(x, None, dy, want_bias=False)
+    assert torch.equal(dw, dw2)
+
+
+def test_bn_buffers_must_be_fp32_and_momentum_none_rejected(cuda_dev):
+    net = DoubleConv(16, 16, dropout_rate=0.0).cuda().to(torch.bfloat16)      # model.to(bfloat16): buffers become bf16
+    with pytest.raises(TypeError, match="running_mean"):
+        net(torch.randn(1, 16, 8, 8, 8, device="cuda", dtype=torch.bfloat16))
+    net = DoubleConv(16, 16, dropout_rate=0.0).cuda()
+    net.double_conv[1].momentum = None
+    with pytest.raises(ValueError, match="momentum=None"):
+        net(torch.randn(1, 16, 8, 8, 8, device="cuda"))
+
+
+def test_bias_free_layers_backward(cuda_dev):
+    """bias=None layers: autograd must receive None (not a tensor) for the missing bias."""
+    x = torch.randn(1, 4, 4, 4, 16, device="cuda", requires_grad=True)
+    w = torch.randn(4, 16, 1, 1, 1, device="cuda", requires_grad=True)
+    F.final_conv1x1(x, w, None).sum().backward()
+    assert w.grad is not None and x.grad is not None
+    wt = torch.randn(16, 8, 2, 2, 2, device="cuda", requires_grad=True)
+    x2 = torch.randn(1, 4, 4, 4, 16, device="cuda", requires_grad=True)
+    F.conv_transpose2(x2, wt, None).sum().backward()
+    assert wt.grad is not None and x2.grad is not None

@@ -151,3 +151,22 @@ def test_dann_head_matches_reference(golden_dir):
     np.testing.assert_allclose(ft.grad.numpy(), g["grad_ft"], rtol=1e-4, atol=1e-8)
     for k in p:
         np.testing.assert_allclose(p[k].grad.numpy(), g["grad/" + k], rtol=1e-4, atol=1e-8)
+
+
+BINARY_CASES = ["a", "b", "c", "empty_target", "full_target"]
+
+
+@pytest.mark.parametrize("case", BINARY_CASES)
+def test_binary_helpers_match_reference(golden_dir, case):
+    """utils/metrics.py:6-12, 42-63, 131-135 (oracle/make_golden_binary.py ran the reference)."""
+    g = np.load(os.path.join(golden_dir, "binary_helpers.npz"))
+    prob, tgt = torch.from_numpy(g[f"{case}/prob"]), torch.from_numpy(g[f"{case}/target"])
+    assert OM.dice_score(prob, tgt) == float(g[f"{case}/dice_score"])
+    assert OM.iou_score(prob, tgt) == float(g[f"{case}/iou_score"])
+    assert OM.accuracy_score(prob, tgt) == float(g[f"{case}/accuracy_score"])
+    z = torch.from_numpy(g[f"{case}/logits"]).requires_grad_(True)
+    loss = OM.dice_loss(z, tgt)
+    loss.backward()
+    assert abs(float(loss) - float(g[f"{case}/dice_loss"])) <= 1e-6
+    ref = torch.from_numpy(g[f"{case}/dice_loss_grad"])
+    assert (z.grad - ref).abs().max() <= 1e-6 * max(1.0, float(ref.abs().max()))
