@@ -101,6 +101,15 @@ int b200_conv3d_k3(int dtype, int impl, const void* x0, int c0, const void* x1, 
                    const void* wpack, const float* bias, void* y0, int co0, void* y1, int co1,
                    int N, int D, int H, int W, void* stream);
 
+/* Convolution + BatchNorm3d batch statistics in one kernel (reference models/unet.py:11-12, :15-16: nn.Conv3d -> nn.BatchNorm3d
+ * in training mode).  b200_conv3d_k3_bnstats_blocks() returns how many partial rows the fused kernel writes for a problem, or 0
+ * when it does not apply (then call b200_conv3d_k3 + b200_bn_stats).  b200_conv3d_k3_bnstats() writes y0 and
+ * partials[rows][2][co0] fp32 = per-CTA (sum, sum of squares) of (y - bias) over the bf16 values stored; finish with
+ * b200_bn_finalize_ex(partials, rows, bias, ...).  partials must hold b200_bn_partials_bytes(co0). */
+int b200_conv3d_k3_bnstats_blocks(int dtype, int impl, int c0, int c1, int co0, int co1, int N, int D, int H, int W);
+int b200_conv3d_k3_bnstats(int dtype, int impl, const void* x0, int c0, const void* x1, int c1, const void* wpack,
+                           const float* bias, void* y0, int co0, int N, int D, int H, int W, float* partials, void* stream);
+
 /* weight gradient of nn.Conv3d(k=3,p=1): dw[Cout, Cin, 3,3,3] fp32 (torch layout, overwritten),
  * dbias[Cout] fp32 (may be NULL).  workspace: b200_conv3d_wgrad_workspace() bytes. */
 int64_t b200_conv3d_wgrad_workspace(int c0, int c1, int Cout, int N, int D, int H, int W);
@@ -130,6 +139,11 @@ int b200_bn_finalize(int dtype, const void* x, const float* partials, int64_t M,
                      float eps, float momentum, int training, float* running_mean, float* running_var,
                      int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* invstd,
                      void* stream);
+/* training-mode finalize over `nblocks` partial rows whose sums were taken around shift_vec[c] (NULL = 0): for the partials of
+ * b200_conv3d_k3_bnstats pass its row count and the convolution bias. */
+int b200_bn_finalize_ex(const float* partials, int nblocks, const float* shift_vec, int64_t M, int C, const float* gamma,
+                        const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                        int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* invstd, void* stream);
 /* y = dropmask[n,c] * relu((x - mean[c])*scale[c] + shift[c]);  dropmask NULL = no dropout;
  * x: [N, S, C] rows, y same. relu: 0/1. */
 int b200_bn_act_fwd(int dtype, const void* x, void* y, const float* scale, const float* shift, const float* mean,

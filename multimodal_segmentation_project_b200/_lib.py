@@ -50,6 +50,8 @@ def _declare(lib) -> None:
         "b200_conv3d_k3_select": (I, [I, I, I, I, I, I, I, I, I, I]),
         "b200_set_conv_persistent": (I, [I]),
         "b200_conv3d_k3": (I, [I, I, P, I, P, I, P, P, P, I, P, I, I, I, I, I, P]),
+        "b200_conv3d_k3_bnstats_blocks": (I, [I, I, I, I, I, I, I, I, I, I]),
+        "b200_conv3d_k3_bnstats": (I, [I, I, P, I, P, I, P, P, P, I, I, I, I, I, P, P]),
         "b200_conv3d_wgrad_workspace": (L, [I, I, I, I, I, I, I]),
         "b200_set_wgrad_impl": (I, [I]),
         "b200_debug_fail_next_wgrad": (I, [I]),
@@ -57,6 +59,7 @@ def _declare(lib) -> None:
         "b200_bn_partials_bytes": (L, [I]),
         "b200_bn_stats": (I, [I, P, L, I, P, P]),
         "b200_bn_finalize": (I, [I, P, P, L, I, P, P, F, F, I, P, P, P, P, P, P, P, P]),
+        "b200_bn_finalize_ex": (I, [P, I, P, L, I, P, P, F, F, P, P, P, P, P, P, P, P]),
         "b200_bn_act_fwd": (I, [I, P, P, P, P, P, P, I, L, L, I, P]),
         "b200_bn_act_bwd_reduce": (I, [I, P, P, P, P, P, P, P, I, L, L, I, P, P]),
         "b200_bn_bwd_finalize": (I, [P, L, I, P, P, P, P]),

@@ -514,7 +514,9 @@ int b200_pack_conv3_weights_tc2(int mode, const float* w, void* out, int Cout, i
 // persistent variant for layers with many tiles (conv_tc3.cu); same packed weights as tc2
 bool b200_conv3d_k3_tc3_wanted(int c0, int c1, int co0, int co1, int N, int D, int H, int W);
 int b200_conv3d_k3_tc3(const void* x0, int c0, const void* x1, int c1, const void* wpack, const float* bias, void* y0,
-                       int co0, void* y1, int co1, int N, int D, int H, int W, cudaStream_t stream);
+                       int co0, void* y1, int co1, int N, int D, int H, int W, cudaStream_t stream, float* stats = nullptr);
+int b200_conv3d_k3_tc3_stats_blocks(int c0, int c1, int co0, int co1, int N, int D, int H, int W);
+static bool conv_persistent_on(int c0, int c1, int co0, int co1);
 static int g_conv_persistent = -1;  // -1 unset (env B200_CONV_PERSISTENT or 1), 0 never, 1 auto, 2 whenever the layer has enough tiles
 static int tc_version() {
   static int v = -1;
@@ -610,15 +612,9 @@ extern "C" int b200_conv3d_k3(int dtype, int impl, const void* x0, int c0, const
     B200_REQUIRE(b200_conv3d_k3_tc_supported(c0, c1, co0, co1, N, D, H, W), B200_ERR_UNSUPPORTED,
                  "conv3d_k3(tcgen05): channels (%d+%d)->(%d+%d) need multiples of 16 (Cout <= 128 or a multiple of 128)", c0, c1, co0, co1);
     if (tc_version() == 2) {
-      // The persistent kernel (conv_tc3.cu) and the two-CTA-per-SM kernel (conv_tc2.cu) are both bound by the tensor core's
-      // serialized operand fetch (T_mma ~ A wavefronts + B wavefronts + N/2).
-      // In isolation the two kernels are within a few percent of each other except for 16->16 (persistent: 121 vs 129 us);
-      // inside the train step, where the side-stream weight gradients compete for the SMs, the persistent kernel is the
-      // better neighbour for every layer with enough tiles (A/B on one box: 4.91 -> 4.79..4.87 ms/step), so "auto" uses it
-      // wherever b200_conv3d_k3_tc3_wanted() says the layer has >= 2 tiles per SM.  Mode 3 = the old 16->16-only policy.
-      if (g_conv_persistent < 0) { const char* e = getenv("B200_CONV_PERSISTENT"); g_conv_persistent = e ? atoi(e) : 1; }
-      const bool want = g_conv_persistent == 1 || g_conv_persistent == 2 || (g_conv_persistent == 3 && c0 + c1 == 16 && co0 + co1 == 16);
-      if (want && b200_conv3d_k3_tc3_wanted(c0, c1, co0, co1, N, D, H, W))
+      // The persistent kernel (conv_tc3.cu: two MMA-issuing warps, double-buffered TMEM) serves every layer with >= 2 tiles per
+      // SM; the two-CTA-per-SM kernel (conv_tc2.cu, split-K) the deep layers.  Mode 3 = the old 16->16-only policy.
+      if (conv_persistent_on(c0, c1, co0, co1) && b200_conv3d_k3_tc3_wanted(c0, c1, co0, co1, N, D, H, W))
         return b200_conv3d_k3_tc3(x0, c0, x1, c1, wpack, bias, y0, co0, y1, co1, N, D, H, W, st);
       return b200_conv3d_k3_tc2(x0, c0, x1, c1, wpack, bias, y0, co0, y1, co1, N, D, H, W, st);
     }
@@ -646,6 +642,29 @@ extern "C" int b200_conv3d_k3(int dtype, int impl, const void* x0, int c0, const
   if (dtype == B200_BF16) RUN(__nv_bfloat16);
 #undef RUN
   B200_FAIL(B200_ERR_UNSUPPORTED, "conv3d_k3: unknown dtype %d", dtype);
+}
+
+static bool conv_persistent_on(int c0, int c1, int co0, int co1) {
+  if (g_conv_persistent < 0) { const char* e = getenv("B200_CONV_PERSISTENT"); g_conv_persistent = e ? atoi(e) : 1; }
+  return g_conv_persistent == 1 || g_conv_persistent == 2 || (g_conv_persistent == 3 && c0 + c1 == 16 && co0 + co1 == 16);
+}
+
+// Convolution + BatchNorm batch statistics in one kernel (models/unet.py:11-12 / :15-16): the persistent tcgen05 kernel's epilogue
+// accumulates sum / sum of squares of (y - bias) per channel over the bf16 values it stores.  Returns the number of partial rows
+// written to `partials` ([rows][2][Cout] fp32, the layout of b200_bn_stats) — pass it, with shift = bias, to b200_bn_finalize_ex.
+extern "C" int b200_conv3d_k3_bnstats_blocks(int dtype, int impl, int c0, int c1, int co0, int co1, int N, int D, int H, int W) {
+  if (dtype != B200_BF16 || impl != 2 || tc_version() != 2 || !b200_conv3d_k3_tc_supported(c0, c1, co0, co1, N, D, H, W)) return 0;
+  if (!conv_persistent_on(c0, c1, co0, co1)) return 0;
+  return b200_conv3d_k3_tc3_stats_blocks(c0, c1, co0, co1, N, D, H, W);
+}
+
+extern "C" int b200_conv3d_k3_bnstats(int dtype, int impl, const void* x0, int c0, const void* x1, int c1, const void* wpack,
+                                      const float* bias, void* y0, int co0, int N, int D, int H, int W, float* partials, void* stream) {
+  B200_REQUIRE(x0 && wpack && y0 && partials, B200_ERR_SHAPE, "conv3d_k3_bnstats: null pointer");
+  B200_REQUIRE((c1 == 0) == (x1 == nullptr), B200_ERR_SHAPE, "conv3d_k3_bnstats: second tensor / channel count mismatch");
+  B200_REQUIRE(b200_conv3d_k3_bnstats_blocks(dtype, impl, c0, c1, co0, 0, N, D, H, W) > 0, B200_ERR_UNSUPPORTED,
+               "conv3d_k3_bnstats: the fused-statistics kernel does not serve this problem (ask b200_conv3d_k3_bnstats_blocks first)");
+  return b200_conv3d_k3_tc3(x0, c0, x1, c1, wpack, bias, y0, co0, nullptr, 0, N, D, H, W, (cudaStream_t)stream, partials);
 }
 
 extern "C" int b200_set_conv_persistent(int mode) {

@@ -118,24 +118,27 @@ conv3d_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tm0, co
   if (warp == 0) {
     // ===================== activation stages by TMA =====================
     if (lane == 0) {
+      // (slab, plane, ring slot, phase) as counters: divisions by run-time values are long dependent chains in a lone thread
+      int s = 0, q = -1, st = 0;
+      uint32_t ph = 1;
       for (int it = 0; it < total_stages; ++it) {
-        const int s = it / nq, q = it % nq - 1;
-        const int st = it % p.stages;
-        tc::mbar_wait(a_empty(st), ((it / p.stages) & 1) ^ 1);
+        tc::mbar_wait(a_empty(st), ph);
         tc::mbar_arrive_expect_tx(a_full(st), kStageTx);
         const int c = (slab0 + s) * 16;
         const CUtensorMap* tm = c < p.c0 ? &tm0 : &tm1;
         const int cc = c < p.c0 ? c : c - p.c0;
         const uint32_t dst = tc::smem_u32(act + st * kStageBytes);
         tma_load_5d(dst, tm, cc, w0 - 1, h0 - 1, d0 + q, n, a_full(st));
+        if (++q > planes) { q = -1; ++s; }
+        if (++st == p.stages) { st = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ===================== weight slabs by TMA bulk copy =====================
     if (lane == 0) {
       for (int s = 0; s < nslabs; ++s) {
-        const int ws = s % p.wstages;
-        tc::mbar_wait(w_empty(ws), ((s / p.wstages) & 1) ^ 1);
+        const int ws = p.wstages == 2 ? (s & 1) : 0;
+        tc::mbar_wait(w_empty(ws), ((p.wstages == 2 ? (s >> 1) : s) & 1) ^ 1);
         tc::mbar_arrive_expect_tx(w_full(ws), wbytes);
         tc::bulk_g2s(tc::smem_u32(wts + (size_t)ws * wbytes), p.wpack + ((size_t)nchunk * p.slabs + slab0 + s) * wbytes, wbytes, w_full(ws));
       }
@@ -157,18 +160,19 @@ conv3d_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tm0, co
       for (int i = 1; i <= 3; ++i) idesc_n[i] = tc::idesc_bf16_f32(128, (int)(i * n_t));
       const bool wt1 = w0 + 8 < p.W;
       const uint32_t wt_cols = (uint32_t)p.dseg * n_t;
+      int st = 0;
+      uint32_t ph = 0;
+      const uint32_t act16 = tc::smem_u32(act) >> 4;
       for (int s = 0; s < nslabs; ++s) {
-        const int ws = s % p.wstages;
-        tc::mbar_wait(w_full(ws), (s / p.wstages) & 1);
+        const int ws = p.wstages == 2 ? (s & 1) : 0;
+        tc::mbar_wait(w_full(ws), (p.wstages == 2 ? (s >> 1) : s) & 1);
         tc::tc_fence_after();
         const uint32_t w_lo = b_lo0 + (tc::smem_u32(wts + (size_t)ws * wbytes) >> 4);
         for (int qi = 0; qi < nq; ++qi) {
-          const int it = s * nq + qi;
-          const int st = it % p.stages;
-          tc::mbar_wait(a_full(st), (it / p.stages) & 1);
+          tc::mbar_wait(a_full(st), ph);
           tc::tc_fence_after();
           const int q = qi - 1;
-          const uint32_t a_lo = a_lo0 + (tc::smem_u32(act + st * kStageBytes) >> 4);
+          const uint32_t a_lo = a_lo0 + act16 + (uint32_t)st * (kStageBytes >> 4);
           // valid kd for this input plane: output plane pl = q + 1 - kd in [0, planes)
           const int kd_lo = max(0, q + 2 - planes), kd_hi = min(2, q + 1);
           // kd groups of at most kd_per_mma taps; planes q+1-a .. q+1-b occupy ascending TMEM column blocks
@@ -203,6 +207,7 @@ conv3d_tc2_kernel(const Tc2Params p, const __grid_constant__ CUtensorMap tm0, co
           }
           tc::umma_commit(a_empty(st));
           if (s == nslabs - 1 && q >= 1) tc::umma_commit(acc_full(q - 1));
+          if (++st == p.stages) { st = 0; ph ^= 1u; }
         }
         tc::umma_commit(w_empty(ws));
       }

@@ -16,6 +16,8 @@
 // Build with `make EXTRA=-DB200_TC_DEBUG` for per-role cycle counters (env B200_TC_DEBUG=1 prints them) and for the
 // bottleneck knobs of env B200_TC3_SKIP (bit 0: no MMAs, 1: no epilogue global stores, 2: no epilogue TMEM loads,
 // 3: no TMA activation loads after the first ring fill).  The default build contains none of this.
+// What these knobs found (profiles/r02_tc3_bottleneck.md): the kernel was paced by the MMA-issuing warp's own
+// per-stage bookkeeping, not by the tensor core.
 #ifdef B200_TC_DEBUG
 #define TC3_DBG(...) __VA_ARGS__
 #define TC3_CLOCK() clock64()
@@ -33,7 +35,7 @@ constexpr int kPlaneVox = kHalo * kHalo;
 constexpr int kStageBytes = 10496;                  // 324 voxels x 32 B rounded up to the 256-byte swizzle period
 constexpr int kStageTx = kPlaneVox * 32;
 constexpr int kMaxStages = 12;
-constexpr int kThreads = 384;                       // w0: act TMA, w1: weight TMA + TMEM alloc, w2: MMA, w4-11: epilogue
+constexpr int kThreads = 384;                       // w0: act TMA, w1: weight TMA + TMEM alloc, w2/w3: MMA issue (one per w-tile), w4-11: epilogue
 constexpr int kMaxDseg = 8;
 constexpr int kSmemHeader = 1024;
 constexpr int kSetCols = 256;                       // TMEM columns per accumulator set
@@ -48,6 +50,7 @@ struct Tc3Params {
   int wstationary;   // all slabs resident in shared memory (requires nchunks == 1)
   int wstages;       // streaming mode: ring depth (1 or 2)
   int total_tiles;
+  float* stats;             // STATS_CH kernels: per-CTA BatchNorm partial sums [grid][2][Cout] (sum, sum of squares of y - bias)
   unsigned long long* dbg;  // optional per-CTA cycle counters (B200_TC_DEBUG builds): [cta][8]
   int skip;                 // B200_TC_DEBUG builds: bottleneck knobs (see top of file)
 };
@@ -73,6 +76,11 @@ __device__ __forceinline__ uint64_t desc_kmajor_sw32(uint32_t addr, uint32_t sbo
   return d;
 }
 
+// STATS_CH = 0: plain convolution.  STATS_CH = 16 / 32 (= Cout): the epilogue also accumulates, per output channel, the sum
+// and the sum of squares of (y - bias) over the voxels it stores — y being the bf16-ROUNDED value the next kernel will read,
+// which is what the reference's BatchNorm sees (models/unet.py:12,16 under autocast) — and the CTA writes one partial row in
+// the layout of bn_stats (elementwise_kernels.cu).  This removes one full read of the activation per layer.
+template <int STATS_CH>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -96,10 +104,10 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
   const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 2 && lane == 0) {
-    for (int i = 0; i < kMaxStages; ++i) { tc::mbar_init(a_full(i), 1); tc::mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(w_full(i), 1); tc::mbar_init(w_empty(i), 1); }
+    for (int i = 0; i < kMaxStages; ++i) { tc::mbar_init(a_full(i), 1); tc::mbar_init(a_empty(i), 2); }   // a_empty: both issuing warps
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(w_full(i), 1); tc::mbar_init(w_empty(i), 2); }
     for (int s = 0; s < 2; ++s) {
-      for (int i = 0; i < kMaxDseg; ++i) tc::mbar_init(acc_full(s, i), 1);
+      for (int i = 0; i < kMaxDseg; ++i) tc::mbar_init(acc_full(s, i), 2);   // both issuing warps commit
       tc::mbar_init(acc_empty(s), 8);  // one arrival per epilogue warp
     }
     tc::fence_barrier_init();
@@ -117,11 +125,14 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
   tc::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // shuffle from a constant lane: provably warp-uniform (uniform registers)
 
-  if (warp == 0 TC3_DBG(&& !(p.skip & 128))) {
+  if (warp == 0) {
     // ===================== activation stages by TMA, continuous across tiles =====================
     {
-      int it = 0;
-      TC3_DBG(long long dbg_prod_wait = 0; const long long tstart = clock64();)
+      // ring position / phase kept as counters: a division by the runtime ring depth is a ~25-instruction dependent chain,
+      // and this warp has no other warp to hide it behind
+      int st = 0;
+      uint32_t ph = 1;          // producer waits for the "previous" phase of a_empty: passes immediately on the first lap
+      TC3_DBG(int it = 0; long long dbg_prod_wait = 0; const long long tstart = clock64();)
       for (int k = 0; k < my_tiles; ++k) {
         const Tile t = decode_tile(p, blockIdx.x + k * gridDim.x);
         const int w0 = t.tw * 16, h0 = t.th * 16, d0 = t.db * p.dseg;
@@ -130,10 +141,9 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
           const int c = s * 16;
           const CUtensorMap* tm = c < p.c0 ? &tm0 : &tm1;
           const int cc = c < p.c0 ? c : c - p.c0;
-          for (int q = -1; q <= planes; ++q, ++it) {
-            const int st = it % p.stages;
+          for (int q = -1; q <= planes; ++q) {
             TC3_DBG(const long long t0 = clock64();)
-            tc::mbar_wait(a_empty(st), ((it / p.stages) & 1) ^ 1);
+            tc::mbar_wait(a_empty(st), ph);
             TC3_DBG(dbg_prod_wait += clock64() - t0;)
             if (tc::elect_one()) {
 #ifdef B200_TC_DEBUG
@@ -146,6 +156,8 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
               }
             }
             __syncwarp();
+            TC3_DBG(++it;)
+            if (++st == p.stages) { st = 0; ph ^= 1u; }
           }
         }
       }
@@ -163,41 +175,46 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
         for (int k = 0; k < my_tiles; ++k) {
           const Tile t = decode_tile(p, blockIdx.x + k * gridDim.x);
           for (int s = 0; s < p.slabs; ++s, ++wi) {
-            const int ws = wi % p.wstages;
-            tc::mbar_wait(w_empty(ws), ((wi / p.wstages) & 1) ^ 1);
+            const int ws = p.wstages == 2 ? (wi & 1) : 0;
+            tc::mbar_wait(w_empty(ws), (((p.wstages == 2 ? (wi >> 1) : wi) & 1) ^ 1));
             tc::mbar_arrive_expect_tx(w_full(ws), wbytes);
             tc::bulk_g2s(tc::smem_u32(wts + (size_t)ws * wbytes), p.wpack + ((size_t)t.nchunk * p.slabs + s) * wbytes, wbytes, w_full(ws));
           }
         }
       }
     }
-  } else if (warp == 2) {
-    // ===================== MMA issue: the whole warp runs the loop, one elected lane issues =====================
+  } else if (warp == 2 || warp == 3) {
+    // ===================== MMA issue: TWO issuing warps, one per w-tile (accumulator columns [wt * wt_cols, +wt_cols)) ===========
+    // tcgen05.mma issue blocks once a few instructions are queued, so whatever the issuing warp does between two stages
+    // (barrier wait, fence, descriptor arithmetic: ~300 exposed-latency cycles) leaves the tensor core idle.  With the two
+    // w-tiles issued by two warps, one warp's bookkeeping overlaps the other warp's MMAs (measured on the 16 -> 16 layer at
+    // 2 x 128^3 with the MMAs as the only work: 1 issuer 106 us, 2 issuers 90 us; forcing the two warps half a stage apart
+    // with a handshake was slower again: 100 us).  Both warps wait on the same stage barriers and both commit:
+    // a_empty / w_empty / acc_full count two arrivals.  The whole warp runs the loop, one elected lane issues.
+    const int wt = warp - 2;
     const uint32_t n_t = p.n_tile;
     const uint32_t b_lbo = 48u * n_t, b_tap16 = 6u * n_t;
     const uint64_t a_proto = desc_kmajor_sw32(0, kHalo * 32);
     const uint64_t b_proto = tc::smem_desc_kmajor_noswz(0, b_lbo, 128);
-    const uint32_t a_hi = (uint32_t)(a_proto >> 32), a_lo0 = (uint32_t)a_proto;
+    const uint32_t a_hi = (uint32_t)(a_proto >> 32);
+    const uint32_t a_lo0 = (uint32_t)a_proto + (tc::smem_u32(act) >> 4) + (uint32_t)wt * 16u;   // + 8 voxels for the second w-tile
     const uint32_t b_hi = (uint32_t)(b_proto >> 32), b_lo0 = (uint32_t)b_proto;
     const uint32_t idesc0 = tc::idesc_bf16_f32(128, 0);       // N field added per MMA: (N >> 3) << 17
     const uint32_t idesc_step = (n_t >> 3) << 17;             // one more kd block
     const uint32_t wt_cols = (uint32_t)p.dseg * n_t;
     if (p.wstationary) { tc::mbar_wait(w_full(0), 0); tc::tc_fence_after(); }
-    int it = 0, wi = 0;
+    int st = 0, wi = 0;
+    uint32_t ph = 0;
     TC3_DBG(long long dbg_wait_full = 0, dbg_wait_acc = 0; const long long tstart = clock64();)
     for (int k = 0; k < my_tiles; ++k) {
       const Tile t = decode_tile(p, blockIdx.x + k * gridDim.x);
       const int w0 = t.tw * 16, d0 = t.db * p.dseg;
       const int planes = min(p.dseg, p.D - d0);
-#ifdef B200_TC_DEBUG
-      const bool wt1_ = w0 + 8 < p.W;
-#else
-      const bool wt1 = w0 + 8 < p.W;
-#endif
+      const bool active = w0 + wt * 8 < p.W TC3_DBG(&& !(p.skip & 1));   // a w-tile entirely outside the volume only keeps the barriers moving
       const int set = k & 1;
-      const uint32_t tset = tmem_base + (uint32_t)set * kSetCols;
+      const uint32_t tset = tmem_base + (uint32_t)set * kSetCols + (uint32_t)wt * wt_cols;
       TC3_DBG(const long long ta = clock64();)
-      if (true TC3_DBG(&& !(p.skip & 512))) tc::mbar_wait(acc_empty(set), ((k >> 1) & 1) ^ 1);   // epilogue of tile k-2 has drained this set
+      tc::mbar_wait(acc_empty(set), ((k >> 1) & 1) ^ 1);   // epilogue of tile k-2 has drained this set
       TC3_DBG(dbg_wait_acc += clock64() - ta;)
       tc::tc_fence_after();
       for (int s = 0; s < p.slabs; ++s) {
@@ -206,67 +223,49 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
         if (p.wstationary) {
           w_lo = b_lo0 + (tc::smem_u32(wts + (size_t)s * wbytes) >> 4);
         } else {
-          ws = wi % p.wstages;
-          tc::mbar_wait(w_full(ws), (wi / p.wstages) & 1);
+          ws = p.wstages == 2 ? (wi & 1) : 0;
+          tc::mbar_wait(w_full(ws), (p.wstages == 2 ? (wi >> 1) : wi) & 1);
           tc::tc_fence_after();
           w_lo = b_lo0 + (tc::smem_u32(wts + (size_t)ws * wbytes) >> 4);
           ++wi;
         }
-        for (int q = -1; q <= planes; ++q, ++it) {
-          const int st = it % p.stages;
+        const bool last_slab = s == p.slabs - 1;
+        for (int q = -1; q <= planes; ++q) {
           TC3_DBG(const long long tf = clock64();)
-          if (true TC3_DBG(&& !(p.skip & 128))) tc::mbar_wait(a_full(st), (it / p.stages) & 1);
+          tc::mbar_wait(a_full(st), ph);
           TC3_DBG(dbg_wait_full += clock64() - tf;)
           tc::tc_fence_after();
-          uint32_t a_lo = a_lo0 + (tc::smem_u32(act + st * kStageBytes) >> 4);
-          TC3_DBG(if (p.skip & 32) a_lo = a_lo0 + (tc::smem_u32(act) >> 4);)
-          TC3_DBG(const bool wt1 = wt1_ && !(p.skip & 16);)
+          const uint32_t a_lo = a_lo0 + (uint32_t)st * (kStageBytes >> 4);
           const int kd_lo = max(0, q + 2 - planes), kd_hi = min(2, q + 1);
           const bool first = (s == 0 && kd_lo == 0);
           if (tc::elect_one()) {
-#ifdef B200_TC_DEBUG
-            if (p.skip & 1) {
-              tc::umma_commit(a_empty(st));
-              if (s == p.slabs - 1 && q >= 1) tc::umma_commit(acc_full(set, q - 1));
-            } else {
-#endif
-            if (first) {
-              // tap (0,0), kd = 0: the plane's very first contribution overwrites its accumulator
-              const uint32_t col = tset + (uint32_t)(p.dseg - 2 - q) * n_t;
-              const uint32_t id1 = idesc0 + idesc_step;
-              tc::umma_bf16_ss(col, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | w_lo, id1, 0);
-              if (wt1) tc::umma_bf16_ss(col + wt_cols, ((uint64_t)a_hi << 32) | (a_lo + 16), ((uint64_t)b_hi << 32) | w_lo, id1, 0);
-              if (kd_hi >= 1) {
-                const uint64_t bd = ((uint64_t)b_hi << 32) | (w_lo + n_t);
-                const uint32_t idr = idesc0 + idesc_step * (uint32_t)kd_hi;
-                tc::umma_bf16_ss(col + n_t, ((uint64_t)a_hi << 32) | a_lo, bd, idr, 1);
-                if (wt1) tc::umma_bf16_ss(col + wt_cols + n_t, ((uint64_t)a_hi << 32) | (a_lo + 16), bd, idr, 1);
+            if (active) {
+              if (first) {
+                // tap (0,0), kd = 0: the plane's very first contribution overwrites its accumulator
+                const uint32_t col = tset + (uint32_t)(p.dseg - 2 - q) * n_t;
+                tc::umma_bf16_ss(col, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | w_lo, idesc0 + idesc_step, 0);
+                if (kd_hi >= 1)
+                  tc::umma_bf16_ss(col + n_t, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | (w_lo + n_t),
+                                   idesc0 + idesc_step * (uint32_t)kd_hi, 1);
               }
-            }
-            for (int a = kd_lo; a <= kd_hi; a += p.kd_per_mma) {
-              const int cnt = min(kd_hi, a + p.kd_per_mma - 1) - a + 1;
-              uint32_t col = tset + (uint32_t)(p.dseg - 2 - q + a) * n_t;
-              TC3_DBG(if (p.skip & 256) col = tset;)
-              const uint32_t idesc = idesc0 + idesc_step * (uint32_t)cnt;
-              const uint32_t b_lo_g = w_lo + (uint32_t)a * n_t;
+              for (int a = kd_lo; a <= kd_hi; a += p.kd_per_mma) {
+                const int cnt = min(kd_hi, a + p.kd_per_mma - 1) - a + 1;
+                const uint32_t col = tset + (uint32_t)(p.dseg - 2 - q + a) * n_t;
+                const uint32_t idesc = idesc0 + idesc_step * (uint32_t)cnt;
+                const uint32_t b_lo_g = w_lo + (uint32_t)a * n_t;
 #pragma unroll
-              for (int tap = 0; tap < 9; ++tap) {
-                if (first && tap == 0) continue;
-                uint32_t a_off = (uint32_t)(((tap / 3) * kHalo + (tap % 3)) * 32) >> 4;
-                TC3_DBG(if (p.skip & 32) a_off = 0;)
-                uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo_g + (uint32_t)tap * b_tap16);
-                TC3_DBG(if (p.skip & 64) bd = ((uint64_t)b_hi << 32) | b_lo_g;)
-                tc::umma_bf16_ss(col, ((uint64_t)a_hi << 32) | (a_lo + a_off), bd, idesc, 1);
-                if (wt1) tc::umma_bf16_ss(col + wt_cols, ((uint64_t)a_hi << 32) | (a_lo + a_off + 16), bd, idesc, 1);
+                for (int tap = 0; tap < 9; ++tap) {
+                  if (first && tap == 0) continue;
+                  const uint32_t a_off = (uint32_t)(((tap / 3) * kHalo + (tap % 3)) * 32) >> 4;
+                  tc::umma_bf16_ss(col, ((uint64_t)a_hi << 32) | (a_lo + a_off), ((uint64_t)b_hi << 32) | (b_lo_g + (uint32_t)tap * b_tap16), idesc, 1);
+                }
               }
             }
-            if (true TC3_DBG(&& !(p.skip & 128))) tc::umma_commit(a_empty(st));
-            if (s == p.slabs - 1 && q >= 1 TC3_DBG(&& !(p.skip & 512))) tc::umma_commit(acc_full(set, q - 1));
-#ifdef B200_TC_DEBUG
-            }
-#endif
+            tc::umma_commit(a_empty(st));
+            if (last_slab && q >= 1) tc::umma_commit(acc_full(set, q - 1));
           }
           __syncwarp();
+          if (++st == p.stages) { st = 0; ph ^= 1u; }
         }
         if (!p.wstationary) {
           if (tc::elect_one()) tc::umma_commit(w_empty(ws));
@@ -274,13 +273,16 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
         }
       }
     }
-    TC3_DBG(if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 2] = dbg_wait_full; p.dbg[blockIdx.x * 8 + 3] = dbg_wait_acc; p.dbg[blockIdx.x * 8 + 4] = clock64() - tstart; })
-  } else if (warp >= 4 TC3_DBG(&& !(p.skip & 512))) {
+    TC3_DBG(if (p.dbg && lane == 0 && wt == 0) { p.dbg[blockIdx.x * 8 + 2] = dbg_wait_full; p.dbg[blockIdx.x * 8 + 3] = dbg_wait_acc; p.dbg[blockIdx.x * 8 + 4] = clock64() - tstart; })
+  } else if (warp >= 4) {
     // ===================== epilogue: warps 4-7 drain w-tile 0, warps 8-11 w-tile 1 =====================
     const int wt = (warp - 4) >> 2;
     const int ew = warp & 3;
     const int m = ew * 32 + lane;
     int bias_chunk = -1;
+    float st_sum[STATS_CH > 0 ? STATS_CH : 1], st_sq[STATS_CH > 0 ? STATS_CH : 1];
+#pragma unroll
+    for (int i = 0; i < (STATS_CH > 0 ? STATS_CH : 1); ++i) st_sum[i] = st_sq[i] = 0.f;
     TC3_DBG(long long dbg_epi_wait = 0; const long long tstart = clock64();)
     uint32_t full_phase = 0;  // bit (set*8 + plane): parity of the next completion of that acc_full barrier (tiles may have < dseg planes)
     for (int k = 0; k < my_tiles; ++k) {
@@ -310,7 +312,9 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
         tc::tc_fence_after();
         const int64_t row = (((int64_t)t.n * p.D + d0 + pl) * p.H + h) * p.W + w;
         const uint32_t col0 = (uint32_t)(set * kSetCols + (wt * p.dseg + (p.dseg - 1 - pl)) * p.n_tile);
-        for (int cc = 0; cc < p.n_tile / 16; ++cc) {
+#pragma unroll
+        for (int cc = 0; cc < (STATS_CH > 0 ? STATS_CH / 16 : 8); ++cc) {
+          if (STATS_CH == 0 && cc >= p.n_tile / 16) break;
           uint32_t r[16];
           tc::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + col0 + cc * 16, r);
           tc::tmem_ld_wait();
@@ -321,6 +325,15 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
             const float2 bb = *reinterpret_cast<const float2*>(bias_s + cc * 16 + 2 * i);
             __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(r[2 * i]) + bb.x, __uint_as_float(r[2 * i + 1]) + bb.y);
             packed[i] = *reinterpret_cast<uint32_t*>(&hb);
+            if (STATS_CH > 0 && valid) {
+              const float2 yv = __bfloat1622float2(hb);
+              const float d0 = yv.x - bb.x, d1 = yv.y - bb.y;
+              const int c = (STATS_CH > 0 ? cc * 16 + 2 * i : 0);
+              st_sum[c] += d0;
+              st_sq[c] = fmaf(d0, d0, st_sq[c]);
+              st_sum[(STATS_CH > 0 ? c + 1 : 0)] += d1;
+              st_sq[(STATS_CH > 0 ? c + 1 : 0)] = fmaf(d1, d1, st_sq[(STATS_CH > 0 ? c + 1 : 0)]);
+            }
           }
           if (valid TC3_DBG(&& !(p.skip & 2))) {
             bf16* dst = ch < p.co0 ? p.y0 + row * p.co0 + ch : p.y1 + row * p.co1 + (ch - p.co0);
@@ -335,6 +348,24 @@ conv3d_tc3_kernel(const Tc3Params p, const __grid_constant__ CUtensorMap tm0, co
       if (lane == 0) tc::mbar_arrive(acc_empty(set));
     }
     TC3_DBG(if (p.dbg && warp == 4 && lane == 0) { p.dbg[blockIdx.x * 8 + 5] = dbg_epi_wait; p.dbg[blockIdx.x * 8 + 6] = clock64() - tstart; })
+    if (STATS_CH > 0) {
+      // fixed-shape fold: warp butterflies, then the eight epilogue warps in order -> run-to-run deterministic.  The stage ring
+      // is free by now (every accumulator this CTA waited for is complete, so every stage has been consumed): reuse stage 0.
+      float* red = reinterpret_cast<float*>(act);            // [8 warps][2][STATS_CH]
+#pragma unroll
+      for (int c = 0; c < (STATS_CH > 0 ? STATS_CH : 1); ++c) {
+        const float a = warp_sum(st_sum[c]), b = warp_sum(st_sq[c]);
+        if (lane == 0) { red[(warp - 4) * 2 * STATS_CH + c] = a; red[(warp - 4) * 2 * STATS_CH + STATS_CH + c] = b; }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int e = threadIdx.x - 128;
+      if (e < 2 * STATS_CH) {
+        float tot = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) tot += red[wq * 2 * STATS_CH + e];
+        p.stats[(size_t)blockIdx.x * 2 * STATS_CH + e] = tot;
+      }
+    }
   }
 
   tc::tc_fence_before();
@@ -357,8 +388,21 @@ bool b200_conv3d_k3_tc3_wanted(int c0, int c1, int co0, int co1, int N, int D, i
   return tiles >= 2 * B200_NUM_SMS;
 }
 
+// number of per-CTA BatchNorm partial rows the fused-statistics variant writes for this problem (= its grid), 0 when the
+// fused variant does not apply (the caller then runs bn_stats on the output as before)
+int b200_conv3d_k3_tc3_stats_blocks(int c0, int c1, int co0, int co1, int N, int D, int H, int W) {
+  const int cout = co0 + co1;
+  if (co1 != 0 || (cout != 16 && cout != 32)) return 0;
+  if (!b200_conv3d_k3_tc3_wanted(c0, c1, co0, co1, N, D, H, W)) return 0;
+  int dseg = kSetCols / (2 * cout);
+  if (dseg > kMaxDseg) dseg = kMaxDseg;
+  if (dseg > D) dseg = D;
+  const int64_t tiles = (int64_t)((W + 15) / 16) * ((H + 15) / 16) * ((D + dseg - 1) / dseg) * N;
+  return (int)(tiles < B200_NUM_SMS ? tiles : B200_NUM_SMS);
+}
+
 int b200_conv3d_k3_tc3(const void* x0, int c0, const void* x1, int c1, const void* wpack, const float* bias, void* y0, int co0, void* y1,
-                       int co1, int N, int D, int H, int W, cudaStream_t stream) {
+                       int co1, int N, int D, int H, int W, cudaStream_t stream, float* stats) {
   B200_REQUIRE(b200_aligned(x0, 16) && b200_aligned(x1, 16) && b200_aligned(y0, 16) && b200_aligned(y1, 16) && b200_aligned(wpack, 16),
                B200_ERR_ALIGN, "conv3d_k3(tcgen05): pointers must be 16-byte aligned");
   Tc3Params p;
@@ -398,9 +442,14 @@ int b200_conv3d_k3_tc3(const void* x0, int c0, const void* x1, int c1, const voi
   if (c1) { rc = tma::make_ndhwc_map(&tm1, x1, c1, N, D, H, W, kHalo, kHalo); if (rc) return rc; } else tm1 = tm0;
   static bool attr_set = false;
   if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(conv3d_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(conv3d_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(conv3d_tc3_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(conv3d_tc3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
     attr_set = true;
   }
+  p.stats = stats;
+  B200_REQUIRE(!stats || (p.nchunks == 1 && co1 == 0 && (cout == 16 || cout == 32)), B200_ERR_UNSUPPORTED,
+               "conv3d_k3(tcgen05 persistent): fused BatchNorm statistics need Cout = 16 or 32 in one tensor");
   const int grid = p.total_tiles < B200_NUM_SMS ? p.total_tiles : B200_NUM_SMS;
   p.dbg = nullptr;
   p.skip = 0;
@@ -412,7 +461,9 @@ int b200_conv3d_k3_tc3(const void* x0, int c0, const void* x1, int c1, const voi
   }
   { const char* e = getenv("B200_TC3_SKIP"); p.skip = e ? atoi(e) : 0; }
 #endif
-  conv3d_tc3_kernel<<<grid, kThreads, smem, stream>>>(p, tm0, tm1);
+  if (stats && cout == 16) conv3d_tc3_kernel<16><<<grid, kThreads, smem, stream>>>(p, tm0, tm1);
+  else if (stats) conv3d_tc3_kernel<32><<<grid, kThreads, smem, stream>>>(p, tm0, tm1);
+  else conv3d_tc3_kernel<0><<<grid, kThreads, smem, stream>>>(p, tm0, tm1);
   B200_CHECK_LAUNCH("conv3d_k3_tc3");
 #ifdef B200_TC_DEBUG
   if (p.dbg) {

@@ -168,7 +168,7 @@ __device__ __forceinline__ void block_partial_sums(const float* __restrict__ par
 }
 
 template <typename T>
-__global__ void bn_finalize_kernel(const float* __restrict__ partials, const T* __restrict__ x_row0, int nblocks, int64_t M, int C,
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, const T* __restrict__ x_row0, const float* __restrict__ shift_vec, int nblocks, int64_t M, int C,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, int training, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, int64_t* __restrict__ nbt,
@@ -180,7 +180,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, const T* 
   // that the latencies overlap instead of forming a chain behind it (ncu: 8.4 us, almost all of it long-scoreboard stalls)
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
   const float rm0 = running_mean ? running_mean[c] : 0.f, rv0 = running_var ? running_var[c] : 1.f;
-  const float x0 = (training && x_row0) ? to_f32<T>(x_row0[c]) : 0.f;
+  // the shift the partial sums were taken around: row 0 of the tensor (bn_stats) or an explicit vector (fused conv epilogue: the bias)
+  const float x0 = !training ? 0.f : (shift_vec ? shift_vec[c] : (x_row0 ? to_f32<T>(x_row0[c]) : 0.f));
   float mean, var;
   if (training) {
     double sums2[2];
@@ -732,9 +733,23 @@ extern "C" int b200_bn_finalize(int dtype, const void* x, const float* partials,
   const RowMap rm = row_map(M, C);
   B200_REQUIRE(!training || x != nullptr, B200_ERR_SHAPE, "bn_finalize: x (the tensor bn_stats ran on) is required in training mode");
   B200_DISPATCH_DTYPE(dtype, T, (bn_finalize_kernel<T><<<C, kFinThreads, 0, (cudaStream_t)stream>>>(
-                                    partials, (const T*)x, rm.nblocks, M, C, gamma, beta, eps, momentum, training, running_mean, running_var,
+                                    partials, (const T*)x, nullptr, rm.nblocks, M, C, gamma, beta, eps, momentum, training, running_mean, running_var,
                                     num_batches_tracked, scale, shift, mean, invstd)));
   B200_CHECK_LAUNCH("bn_finalize");
+  return B200_OK;
+}
+
+// training-mode finalize over `nblocks` partial rows whose sums were taken around `shift_vec[c]` (NULL = 0): the partials of
+// b200_conv3d_k3_bnstats (nblocks = its return value, shift_vec = the convolution bias)
+extern "C" int b200_bn_finalize_ex(const float* partials, int nblocks, const float* shift_vec, int64_t M, int C, const float* gamma,
+                                   const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                                   int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* invstd, void* stream) {
+  int rc = check_rows("bn_finalize_ex", M, C);
+  if (rc) return rc;
+  B200_REQUIRE(partials && nblocks > 0 && scale && shift && mean && invstd, B200_ERR_SHAPE, "bn_finalize_ex: null pointer / no partial rows");
+  bn_finalize_kernel<float><<<C, kFinThreads, 0, (cudaStream_t)stream>>>(partials, nullptr, shift_vec, nblocks, M, C, gamma, beta, eps, momentum, 1,
+                                                                        running_mean, running_var, num_batches_tracked, scale, shift, mean, invstd);
+  B200_CHECK_LAUNCH("bn_finalize_ex");
   return B200_OK;
 }
 

@@ -221,6 +221,15 @@ def set_conv_persistent(mode: int) -> None:
     check(_lib.load().b200_set_conv_persistent(int(mode)), "set_conv_persistent")
 
 
+_fuse_bn_stats = os.environ.get("B200_FUSE_BN_STATS", "1") != "0"
+
+
+def set_fuse_bn_stats(on: bool) -> None:
+    """Batch statistics from the convolution epilogue (default) or from the separate bn_stats pass (tests / A-B timing)."""
+    global _fuse_bn_stats
+    _fuse_bn_stats = bool(on)
+
+
 def _bn_partials(C, device):
     L = _lib.load()
     return torch.empty(L.b200_bn_partials_bytes(C) // 4, dtype=torch.float32, device=device)
@@ -252,22 +261,34 @@ class _ConvBNAct(torch.autograd.Function):
                                 "the module in float32 and select bf16 compute with torch.autocast or model.compute_dtype")
         impl = conv3d_select_impl(x0, x1, Cout, 0, impl)
         wpack = pack_conv3_weights(weight, pack_mode(impl, False), x0.dtype)
-        conv_out, _ = conv3d_k3_raw(x0, x1, wpack, _f32(bias), Cout, 0, impl)
         M, S = N * D * H * W, D * H * W
         if training and M <= 1:  # same contract as torch.nn.functional.batch_norm
             raise ValueError(f"Expected more than 1 value per channel when training, got input size {[N, Cout, D, H, W]}")
         stats = torch.empty((4, Cout), dtype=torch.float32, device=dev)  # scale, shift, mean, invstd
-        partials = None
-        if training:
+        g32, b32, bias32 = _f32(gamma), _f32(beta), _f32(bias)
+        c0, c1 = x0.shape[-1], (0 if x1 is None else x1.shape[-1])
+        rows = L.b200_conv3d_k3_bnstats_blocks(_dt(x0), impl, c0, c1, Cout, 0, N, D, H, W) if (training and _fuse_bn_stats) else 0
+        if rows > 0:
+            # convolution and batch statistics in ONE kernel: the conv epilogue emits per-CTA (sum, sum of squares) of (y - bias)
             partials = _bn_partials(Cout, dev)
-            check(L.b200_bn_stats(_dt(conv_out), _ptr(conv_out), M, Cout, _ptr(partials), _stream()), "bn_stats")
-        g32, b32 = _f32(gamma), _f32(beta)
-        check(
-            L.b200_bn_finalize(_dt(conv_out), _ptr(conv_out), _ptr(partials), M, Cout, _ptr(g32), _ptr(b32), float(eps), float(momentum), int(training),
-                               _ptr(running_mean), _ptr(running_var), _ptr(nbt), _ptr(stats[0]), _ptr(stats[1]),
-                               _ptr(stats[2]), _ptr(stats[3]), _stream()),
-            "bn_finalize",
-        )
+            conv_out = torch.empty((N, D, H, W, Cout), dtype=x0.dtype, device=dev)
+            check(L.b200_conv3d_k3_bnstats(_dt(x0), impl, _ptr(x0), c0, _ptr(x1), c1, _ptr(wpack), _ptr(bias32), _ptr(conv_out), Cout,
+                                           N, D, H, W, _ptr(partials), _stream()), "conv3d_k3_bnstats")
+            check(L.b200_bn_finalize_ex(_ptr(partials), rows, _ptr(bias32), M, Cout, _ptr(g32), _ptr(b32), float(eps), float(momentum),
+                                        _ptr(running_mean), _ptr(running_var), _ptr(nbt), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]),
+                                        _ptr(stats[3]), _stream()), "bn_finalize_ex")
+        else:
+            conv_out, _ = conv3d_k3_raw(x0, x1, wpack, bias32, Cout, 0, impl)
+            partials = None
+            if training:
+                partials = _bn_partials(Cout, dev)
+                check(L.b200_bn_stats(_dt(conv_out), _ptr(conv_out), M, Cout, _ptr(partials), _stream()), "bn_stats")
+            check(
+                L.b200_bn_finalize(_dt(conv_out), _ptr(conv_out), _ptr(partials), M, Cout, _ptr(g32), _ptr(b32), float(eps), float(momentum), int(training),
+                                   _ptr(running_mean), _ptr(running_var), _ptr(nbt), _ptr(stats[0]), _ptr(stats[1]),
+                                   _ptr(stats[2]), _ptr(stats[3]), _stream()),
+                "bn_finalize",
+            )
         y = torch.empty_like(conv_out)
         check(
             L.b200_bn_act_fwd(_dt(conv_out), _ptr(conv_out), _ptr(y), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]), _ptr(dropmask), 1, N, S,

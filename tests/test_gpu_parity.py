@@ -729,3 +729,35 @@ def test_bias_free_layers_backward(cuda_dev):
     x2 = torch.randn(1, 4, 4, 4, 16, device="cuda", requires_grad=True)
     F.conv_transpose2(x2, wt, None).sum().backward()
     assert wt.grad is not None and x2.grad is not None
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 96, 16, 16), (2, 56, 60, 90, 32, 16), (1, 64, 72, 80, 16, 32), (2, 64, 64, 64, 32, 32)])
+def test_conv_epilogue_bn_statistics_match_separate_pass(cuda_dev, shape):
+    """Conv3d -> BatchNorm3d (models/unet.py:11-12): statistics emitted by the persistent conv kernel's epilogue equal the ones
+    the stand-alone bn_stats pass computes on the stored bf16 tensor; ragged tile borders included."""
+    N, D, H, W, Cin, Cout = shape
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = (torch.randn(N, D, H, W, Cin, device="cuda", generator=g) + 0.3).to(torch.bfloat16)
+    conv = torch.nn.Conv3d(Cin, Cout, 3, padding=1).cuda()
+    with torch.no_grad():
+        conv.bias.add_(torch.linspace(-2, 3, Cout, device="cuda"))       # |mean| >> std on some channels
+    outs = []
+    for fused in (True, False):
+        F.set_fuse_bn_stats(fused)
+        try:
+            bn = torch.nn.BatchNorm3d(Cout).cuda()
+            n0 = _lib.launch_count()
+            y = F.conv_bn_act(x, None, conv, bn, None, True)
+            launches = _lib.launch_count() - n0
+        finally:
+            F.set_fuse_bn_stats(True)
+        outs.append((y, bn.running_mean.clone(), bn.running_var.clone(), launches))
+    (yf, mf, vf, lf), (ys, ms, vs, ls) = outs
+    assert lf == ls - 1, (lf, ls)                                       # one pass fewer
+    assert rel_l2(mf, ms) <= 2e-6 and rel_l2(vf, vs) <= 2e-5, (rel_l2(mf, ms), rel_l2(vf, vs))
+    assert rel_l2(yf, ys) <= 1e-3                                       # same bf16 values up to 1-ulp flips from ~1e-6 scale changes
+    # and against torch on the same bf16 conv output (the reference's arithmetic)
+    w = conv.weight.detach().to(torch.bfloat16)
+    ref = torch.nn.functional.conv3d(x.permute(0, 4, 1, 2, 3).float(), w.float(), conv.bias.detach(), padding=1).to(torch.bfloat16).float()
+    assert rel_l2(mf, 0.1 * ref.mean(dim=(0, 2, 3, 4))) <= 2e-3
+    assert rel_l2(vf - 0.9, 0.1 * ref.var(dim=(0, 2, 3, 4), unbiased=True)) <= 5e-3

@@ -18,13 +18,12 @@ def timeit(fn, iters=7, flush=None):
 dev = torch.device("cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 F.set_conv_persistent(1)
-for Cin, Cout in ((16, 16),):
+for Cin, Cout in ((16, 16), (32, 16), (16, 32)):
     x = torch.randn(2, 128, 128, 128, Cin, device=dev).bfloat16()
     w = torch.randn(Cout, Cin, 3, 3, 3, device=dev) * 0.05
     b = torch.randn(Cout, device=dev)
     wp = F.pack_conv3_weights(w, _lib.PACK_FPROP_TC, torch.bfloat16)
-    for skip, name in ((0, "normal"), (12, "MMA only"), (12 | 128 | 512, "MMA only, no ring, no epilogue handshake"),
-                       (12 | 32 | 64 | 128 | 256 | 512, "same + const A B D"), (12 | 16 | 128 | 512, "same, one w-tile"), (1 | 12 | 128 | 512, "empty loops")):
+    for skip, name in ((0, "normal"), (12, "MMA only"), (1, "no MMA"), (1 | 12, "barriers only")):
         os.environ["B200_TC3_SKIP"] = str(skip)
         ms = timeit(lambda: F.conv3d_k3_raw(x, None, wp, b, Cout, 0, impl=2), flush=flush)
         print(f"{Cin:3d}->{Cout:3d} skip={skip:2d} {name:32s} {ms * 1e3:8.1f} us", flush=True)
