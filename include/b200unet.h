@@ -97,6 +97,9 @@ int b200_conv3d_k3_select(int dtype, int impl, int c0, int c1, int co0, int co1,
  * 0 never, 1 auto (default: every layer with >= 2 tiles per SM and <= 64 output channels per tile), 2 same as 1,
  * 3 only 16->16 layers — for tests and benchmarks. */
 int b200_set_conv_persistent(int mode);
+/* the row-streaming tcgen05 convolution (one 128-voxel row per M tile, A operand reused across the three kh taps) serves
+ * full-resolution layers with 16 / 32 output channels: 1 = wherever it applies (default), 0 = never — tests and A/B timing. */
+int b200_set_conv_rowstream(int on);
 int b200_conv3d_k3(int dtype, int impl, const void* x0, int c0, const void* x1, int c1,
                    const void* wpack, const float* bias, void* y0, int co0, void* y1, int co1,
                    int N, int D, int H, int W, void* stream);

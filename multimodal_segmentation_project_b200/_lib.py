@@ -49,6 +49,7 @@ def _declare(lib) -> None:
         "b200_pack_conv3_bytes": (L, [I, I, I, I]),
         "b200_conv3d_k3_select": (I, [I, I, I, I, I, I, I, I, I, I]),
         "b200_set_conv_persistent": (I, [I]),
+        "b200_set_conv_rowstream": (I, [I]),
         "b200_conv3d_k3": (I, [I, I, P, I, P, I, P, P, P, I, P, I, I, I, I, I, P]),
         "b200_conv3d_k3_bnstats_blocks": (I, [I, I, I, I, I, I, I, I, I, I]),
         "b200_conv3d_k3_bnstats": (I, [I, I, P, I, P, I, P, P, P, I, I, I, I, I, P, P]),

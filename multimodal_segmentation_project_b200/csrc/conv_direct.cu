@@ -516,6 +516,12 @@ bool b200_conv3d_k3_tc3_wanted(int c0, int c1, int co0, int co1, int N, int D, i
 int b200_conv3d_k3_tc3(const void* x0, int c0, const void* x1, int c1, const void* wpack, const float* bias, void* y0,
                        int co0, void* y1, int co1, int N, int D, int H, int W, cudaStream_t stream, float* stats = nullptr);
 int b200_conv3d_k3_tc3_stats_blocks(int c0, int c1, int co0, int co1, int N, int D, int H, int W);
+// row-streaming variant for full-resolution layers with 16 / 32 output channels (conv_tc4.cu); same packed weights
+bool b200_conv3d_k3_tc4_wanted(int c0, int c1, int co0, int co1, int N, int D, int H, int W);
+int b200_conv3d_k3_tc4_stats_blocks(int c0, int c1, int co0, int co1, int N, int D, int H, int W);
+int b200_conv3d_k3_tc4(const void* x0, int c0, const void* x1, int c1, const void* wpack, const float* bias, void* y0,
+                       int co0, void* y1, int co1, int N, int D, int H, int W, cudaStream_t stream, float* stats = nullptr);
+void b200_conv3d_k3_tc4_enable(int on);
 static bool conv_persistent_on(int c0, int c1, int co0, int co1);
 static int g_conv_persistent = -1;  // -1 unset (env B200_CONV_PERSISTENT or 1), 0 never, 1 auto, 2 whenever the layer has enough tiles
 static int tc_version() {
@@ -614,6 +620,8 @@ extern "C" int b200_conv3d_k3(int dtype, int impl, const void* x0, int c0, const
     if (tc_version() == 2) {
       // The persistent kernel (conv_tc3.cu: two MMA-issuing warps, double-buffered TMEM) serves every layer with >= 2 tiles per
       // SM; the two-CTA-per-SM kernel (conv_tc2.cu, split-K) the deep layers.  Mode 3 = the old 16->16-only policy.
+      if (conv_persistent_on(c0, c1, co0, co1) && b200_conv3d_k3_tc4_wanted(c0, c1, co0, co1, N, D, H, W))
+        return b200_conv3d_k3_tc4(x0, c0, x1, c1, wpack, bias, y0, co0, y1, co1, N, D, H, W, st);
       if (conv_persistent_on(c0, c1, co0, co1) && b200_conv3d_k3_tc3_wanted(c0, c1, co0, co1, N, D, H, W))
         return b200_conv3d_k3_tc3(x0, c0, x1, c1, wpack, bias, y0, co0, y1, co1, N, D, H, W, st);
       return b200_conv3d_k3_tc2(x0, c0, x1, c1, wpack, bias, y0, co0, y1, co1, N, D, H, W, st);
@@ -655,7 +663,8 @@ static bool conv_persistent_on(int c0, int c1, int co0, int co1) {
 extern "C" int b200_conv3d_k3_bnstats_blocks(int dtype, int impl, int c0, int c1, int co0, int co1, int N, int D, int H, int W) {
   if (dtype != B200_BF16 || impl != 2 || tc_version() != 2 || !b200_conv3d_k3_tc_supported(c0, c1, co0, co1, N, D, H, W)) return 0;
   if (!conv_persistent_on(c0, c1, co0, co1)) return 0;
-  return b200_conv3d_k3_tc3_stats_blocks(c0, c1, co0, co1, N, D, H, W);
+  const int rows = b200_conv3d_k3_tc4_stats_blocks(c0, c1, co0, co1, N, D, H, W);
+  return rows > 0 ? rows : b200_conv3d_k3_tc3_stats_blocks(c0, c1, co0, co1, N, D, H, W);
 }
 
 extern "C" int b200_conv3d_k3_bnstats(int dtype, int impl, const void* x0, int c0, const void* x1, int c1, const void* wpack,
@@ -664,7 +673,15 @@ extern "C" int b200_conv3d_k3_bnstats(int dtype, int impl, const void* x0, int c
   B200_REQUIRE((c1 == 0) == (x1 == nullptr), B200_ERR_SHAPE, "conv3d_k3_bnstats: second tensor / channel count mismatch");
   B200_REQUIRE(b200_conv3d_k3_bnstats_blocks(dtype, impl, c0, c1, co0, 0, N, D, H, W) > 0, B200_ERR_UNSUPPORTED,
                "conv3d_k3_bnstats: the fused-statistics kernel does not serve this problem (ask b200_conv3d_k3_bnstats_blocks first)");
+  if (b200_conv3d_k3_tc4_stats_blocks(c0, c1, co0, 0, N, D, H, W) > 0)
+    return b200_conv3d_k3_tc4(x0, c0, x1, c1, wpack, bias, y0, co0, nullptr, 0, N, D, H, W, (cudaStream_t)stream, partials);
   return b200_conv3d_k3_tc3(x0, c0, x1, c1, wpack, bias, y0, co0, nullptr, 0, N, D, H, W, (cudaStream_t)stream, partials);
+}
+
+/* 0 = never use the row-streaming kernel (conv_tc4.cu), 1 = wherever it applies (default) — tests and A/B timing */
+extern "C" int b200_set_conv_rowstream(int on) {
+  b200_conv3d_k3_tc4_enable(on);
+  return B200_OK;
 }
 
 extern "C" int b200_set_conv_persistent(int mode) {

@@ -230,6 +230,11 @@ def set_fuse_bn_stats(on: bool) -> None:
     _fuse_bn_stats = bool(on)
 
 
+def set_conv_rowstream(on: bool) -> None:
+    """Row-streaming tcgen05 convolution for full-resolution 16 / 32-channel layers (default on; tests and A/B timing)."""
+    check(_lib.load().b200_set_conv_rowstream(int(bool(on))), "set_conv_rowstream")
+
+
 def _bn_partials(C, device):
     L = _lib.load()
     return torch.empty(L.b200_bn_partials_bytes(C) // 4, dtype=torch.float32, device=device)

@@ -731,7 +731,8 @@ def test_bias_free_layers_backward(cuda_dev):
     assert wt.grad is not None and x2.grad is not None
 
 
-@pytest.mark.parametrize("shape", [(2, 64, 64, 96, 16, 16), (2, 56, 60, 90, 32, 16), (1, 64, 72, 80, 16, 32), (2, 64, 64, 64, 32, 32)])
+@pytest.mark.parametrize("shape", [(2, 64, 64, 96, 16, 16), (2, 56, 60, 90, 32, 16), (1, 64, 72, 80, 16, 32), (2, 64, 64, 64, 32, 32),
+                                   (2, 40, 128, 128, 16, 16), (1, 46, 100, 128, 16, 32), (2, 24, 100, 224, 32, 16)])  # the last three: row-streaming kernel
 def test_conv_epilogue_bn_statistics_match_separate_pass(cuda_dev, shape):
     """Conv3d -> BatchNorm3d (models/unet.py:11-12): statistics emitted by the persistent conv kernel's epilogue equal the ones
     the stand-alone bn_stats pass computes on the stored bf16 tensor; ragged tile borders included."""
@@ -761,3 +762,45 @@ def test_conv_epilogue_bn_statistics_match_separate_pass(cuda_dev, shape):
     ref = torch.nn.functional.conv3d(x.permute(0, 4, 1, 2, 3).float(), w.float(), conv.bias.detach(), padding=1).to(torch.bfloat16).float()
     assert rel_l2(mf, 0.1 * ref.mean(dim=(0, 2, 3, 4))) <= 2e-3
     assert rel_l2(vf - 0.9, 0.1 * ref.var(dim=(0, 2, 3, 4), unbiased=True)) <= 5e-3
+
+
+ROWSTREAM_CASES = [
+    # N, D, H, W, c0, c1, co0, co1   — every case has >= 8 * 148 output rows and W >= 96, so the row-streaming kernel serves it
+    (2, 20, 40, 128, 16, 0, 16, 0),     # ragged last d-block (20 = 2*8 + 4), CTA runs crossing (n, d-block) boundaries
+    (1, 33, 48, 128, 16, 16, 16, 0),    # virtual concat (2 slabs), D = 4*8 + 1
+    (1, 12, 110, 128, 32, 0, 16, 16),   # split output (data gradient of the decoder's first conv), n_tile 32 -> 4 planes per accumulator
+    (2, 16, 40, 100, 16, 0, 16, 0),     # W < 128: masked lanes
+    (1, 8, 80, 256, 16, 0, 32, 0),      # two w-tiles, Cout 32
+    (1, 9, 70, 224, 16, 0, 16, 0),      # W = 128 + 96
+]
+
+
+@pytest.mark.parametrize("case", ROWSTREAM_CASES)
+def test_conv3d_rowstream_vs_oracle(cuda_dev, case):
+    """conv_tc4.cu (one 128-voxel row per M tile, collector reuse of A across kh) against fp64 and against the
+    persistent window kernel it replaces on these shapes (same bf16 inputs, fp32 accumulation: <= 1 bf16 ulp apart)."""
+    N, D, H, W, c0, c1, co0, co1 = case
+    Cin, Cout = c0 + c1, co0 + co1
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(N, Cin, D, H, W, generator=gen).bfloat16().float()
+    w = (torch.randn(Cout, Cin, 3, 3, 3, generator=gen) / (27 * Cin) ** 0.5).bfloat16().float()
+    b = torch.randn(Cout, generator=gen)
+    yr = TF.conv3d(x.double(), w.double(), b.double(), padding=1)
+    x0 = cl(x[:, :c0], torch.bfloat16)
+    x1 = cl(x[:, c0:], torch.bfloat16) if c1 else None
+    wp = F.pack_conv3_weights(w.to(cuda_dev), _lib.PACK_FPROP_TC, torch.bfloat16)
+    outs = []
+    for rowstream in (True, False):
+        F.set_conv_rowstream(rowstream)
+        try:
+            y0, y1 = F.conv3d_k3_raw(x0, x1, wp, b.to(cuda_dev), co0, co1, impl=2)
+            torch.cuda.synchronize()
+        finally:
+            F.set_conv_rowstream(True)
+        outs.append(cf(y0) if y1 is None else torch.cat([cf(y0), cf(y1)], dim=1))
+    assert rel_l2(outs[0], yr) <= 4e-3, rel_l2(outs[0], yr)
+    assert rel_l2(outs[0], outs[1]) <= 2e-3
+    assert (outs[0] - outs[1]).abs().max() <= 2.0 ** -7 * yr.abs().max()      # never more than a couple of bf16 ulps anywhere
+    # run-to-run determinism
+    y0b, y1b = F.conv3d_k3_raw(x0, x1, wp, b.to(cuda_dev), co0, co1, impl=2)
+    assert torch.equal(cf(y0b) if y1b is None else torch.cat([cf(y0b), cf(y1b)], dim=1), outs[0])
