@@ -13,6 +13,7 @@ cpu_baseline = the oracle (a port of the reference's PyTorch CPU path) timed on 
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -140,8 +141,9 @@ def run_reference(args):
 
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    total = args.steps + args.warmup
-    patch = 128 if total <= 8 else (96 if total <= 16 else 64)  # bounded sample so the run ends within minutes
+    # bounded sample of the benchmark workload: ONE 128^3 patch per step (the GPU arm's per-GPU batch is two of them); the
+    # patch shape — hence the per-voxel work, cache behaviour and BatchNorm statistics — is the benchmark's own.  ~1-2.5 s/step.
+    patch = PATCH
     sd = init_state_dict(1, CLASSES, seed=0)
     x, y = structured_volume(1, patch, seed=1234)
     for _ in range(args.warmup):
@@ -158,7 +160,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "unet3d_train_128cube_b2_per_gpu", "patch": [PATCH] * 3, "batch_per_gpu": BATCH_PER_GPU, "classes": CLASSES,
-                   "loss": "combined_loss (Dice+CE)", "sample_patch": patch},
+                   "loss": "combined_loss (Dice+CE)", "sample_patch": patch, "sample_batch": 1, "same_patch_shape": True},
         "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -167,29 +169,159 @@ def run_reference(args):
 
 
 # ================================================================================ this repo's arm (GPU)
-def time_top_conv_kernel(dev, iters=20):
-    """CUDA-event time of the dominant kernel: conv3d_tc3_kernel (the persistent tcgen05 convolution) on decoder.3.c0's fprop shape
-    (2 x 128^3, (16+16) -> 16 channels, 115.96 GFLOP), L2 flushed between launches."""
-    from multimodal_segmentation_project_b200 import _lib, functional as F
-    N, S, c0, c1, cout = BATCH_PER_GPU, PATCH, 16, 16, 16
-    x0 = torch.randn(N, S, S, S, c0, device=dev).bfloat16()
-    x1 = torch.randn(N, S, S, S, c1, device=dev).bfloat16()
-    w = torch.randn(cout, c0 + c1, 3, 3, 3, device=dev) * 0.05
-    b = torch.zeros(cout, device=dev)
-    wp = F.pack_conv3_weights(w, _lib.PACK_FPROP_TC, torch.bfloat16)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    F.conv3d_k3_raw(x0, x1, wp, b, cout, 0, impl=2)
-    torch.cuda.synchronize()
+
+def _event_time(fn, flush, iters=10):
+    """median CUDA-event time (ms) of fn() on the current stream, L2 flushed (256 MB write) before every launch"""
+    fn(); torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
         flush.zero_()
         a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); F.conv3d_k3_raw(x0, x1, wp, b, cout, 0, impl=2); e.record()
+        a.record(); fn(); e.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(e))
-    flops = 2.0 * N * S ** 3 * 27 * (c0 + c1) * cout
-    return sum(ts) / len(ts), flops
+    return statistics.median(ts)
 
+
+def time_step_kernels(dev, peaks):
+    """CUDA-event times, measured in THIS run, of the kernels that carry the step at the benchmark shapes (2 x 128^3, top level):
+    tensor-bound ones as TFLOP/s against the measured bf16 burst peak, memory-bound ones as algorithmic GB/s against the measured
+    copy bandwidth (SURVEY.md 8d / DESIGN.md 4 give the bytes per voxel)."""
+    from multimodal_segmentation_project_b200 import _lib, functional as F
+    L = _lib.load()
+    N, S, C = BATCH_PER_GPU, PATCH, 16
+    vox = N * S ** 3
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    a16 = torch.randn(N, S, S, S, C, device=dev).bfloat16()
+    b16 = torch.randn(N, S, S, S, C, device=dev).bfloat16()
+    o16 = torch.empty_like(a16)
+    w32 = torch.randn(16, 32, 3, 3, 3, device=dev) * 0.05
+    bias = torch.zeros(16, device=dev)
+    out = []
+
+    def tensor_row(name, ms, flops):
+        tf = flops / (ms / 1e3) / 1e12
+        out.append({"kernel": name, "ms": ms, "achieved": tf, "unit": "TFLOP/s", "frac": tf / peaks["bf16_burst"], "bound": "tensor"})
+
+    def hbm_row(name, ms, nbytes):
+        gbs = nbytes / (ms / 1e3) / 1e9
+        out.append({"kernel": name, "ms": ms, "achieved": gbs, "unit": "GB/s", "frac": gbs / peaks["hbm"], "bound": "hbm", "bytes": nbytes})
+
+    gf = 2.0 * vox * 27 * 32 * 16
+    wp = F.pack_conv3_weights(w32, _lib.PACK_FPROP_TC, torch.bfloat16)
+    tensor_row("decoder.3.c0 fprop (16+16)->16: conv3d_tc4_kernel", _event_time(lambda: F.conv3d_k3_raw(a16, b16, wp, bias, 16, 0, impl=2), flush), gf)
+    wpd = F.pack_conv3_weights(w32, _lib.PACK_DGRAD_TC, torch.bfloat16)
+    tensor_row("decoder.3.c0 dgrad 16->(16+16): conv3d_tc4_kernel", _event_time(lambda: F.conv3d_k3_raw(a16, None, wpd, None, 16, 16, impl=2), flush), gf)
+    tensor_row("decoder.3.c0 wgrad (16+16)x16: wgrad_tc2_kernel + partial_reduce", _event_time(lambda: F.conv3d_wgrad_raw(a16, b16, o16, want_bias=False), flush), gf)
+    w16 = torch.randn(16, 16, 3, 3, 3, device=dev) * 0.05
+    wp16 = F.pack_conv3_weights(w16, _lib.PACK_FPROP_TC, torch.bfloat16)
+    tensor_row("encoder.0.c1 fprop 16->16: conv3d_tc4_kernel", _event_time(lambda: F.conv3d_k3_raw(a16, None, wp16, bias, 16, 0, impl=2), flush), gf / 2)
+    # BatchNorm passes (bf16, C = 16): apply 2 B read + 2 B write; backward reduce 4 B read; backward apply 4 B read + 2 B write per element
+    stats = torch.rand(4, C, device=dev) + 0.5
+    sums = torch.zeros(2 * C, device=dev)
+    part = torch.empty(L.b200_bn_partials_bytes(C) // 4, device=dev)
+    M = vox
+    hbm_row("bn_act_fwd_kernel", _event_time(lambda: L.b200_bn_act_fwd(1, P(a16), P(o16), P(stats[0]), P(stats[1]), P(stats[2]), None, 1, N, S ** 3, C, st()), flush), 4 * M * C)
+    hbm_row("bn_act_bwd_reduce_kernel", _event_time(lambda: L.b200_bn_act_bwd_reduce(1, P(b16), P(a16), P(stats[0]), P(stats[1]), P(stats[2]), P(stats[3]), None, 1, N, S ** 3, C, P(part), st()), flush), 4 * M * C)
+    hbm_row("bn_act_bwd_apply_kernel", _event_time(lambda: L.b200_bn_act_bwd_apply(1, P(b16), P(a16), P(o16), P(stats[0]), P(stats[1]), P(stats[2]), P(stats[3]), None, 1, P(sums), 1, N, S ** 3, C, st()), flush), 6 * M * C)
+    # head: 1x1x1 conv (2 B x 16 in, 4 B x 4 out), fused loss forward (4C + 8 B / voxel) and backward (+ 4C written), confusion counts
+    wf, bf_ = torch.randn(CLASSES, C, 1, 1, 1, device=dev) * 0.1, torch.zeros(CLASSES, device=dev)
+    logits = torch.randn(N, CLASSES, S, S, S, device=dev)
+    tgt = torch.randint(0, CLASSES, (N, 1, S, S, S), device=dev)
+    hbm_row("conv1x1_fwd_small_kernel", _event_time(lambda: F.final_conv1x1(a16, wf, bf_, round_bf16=True), flush), vox * (2 * C + 4 * CLASSES))
+    lg = logits.clone().requires_grad_(True)
+    hbm_row("seg_loss_fwd_kernel", _event_time(lambda: F.seg_loss(logits, tgt, _lib.LOSS_DICE_CE), flush), vox * (4 * CLASSES + 8))
+    loss = F.seg_loss(lg, tgt, _lib.LOSS_DICE_CE)
+    hbm_row("seg_loss_bwd_kernel", _event_time(lambda: torch.autograd.grad(loss, lg, retain_graph=True), flush), vox * (8 * CLASSES + 8))
+    hbm_row("confusion_kernel", _event_time(lambda: F.confusion_counts(logits, tgt), flush), vox * (4 * CLASSES + 8))
+    return out
+
+
+def time_extra_configs(dev):
+    """BASELINE configs 3-5 on one GPU through the same public API (eager launches, CUDA events, median of 3)."""
+    from multimodal_segmentation_project_b200.inference import evaluate_volume
+    from multimodal_segmentation_project_b200.models.unet import UNet3D
+    from multimodal_segmentation_project_b200.models.unet_dann import UNet3D as UNet3DDann
+    from multimodal_segmentation_project_b200.synthetic import structured_volume
+    from multimodal_segmentation_project_b200.train_dann import DomainDiscriminator, domain_cross_entropy, grad_reverse
+    from multimodal_segmentation_project_b200.utils import metrics as M
+
+    def timed(fn, warm=2, iters=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); e.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(e))
+        return statistics.median(ts)
+
+    torch.manual_seed(0)
+    x, y = structured_volume(2, PATCH, seed=1234)
+    xc, yc = x.to(dev), y.to(dev)
+    vox = 2 * PATCH ** 3
+    out = {}
+    student = UNet3D(1, CLASSES, dropout_rate=0.0).to(dev).train()
+    teacher = UNet3D(1, CLASSES, dropout_rate=0.0).to(dev).eval()
+    for q in teacher.parameters():
+        q.requires_grad = False
+
+    def kd_step():
+        student.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            sl = student(xc)
+            with torch.no_grad():
+                tl = teacher(xc)
+        M.distillation_loss(sl.float(), tl.float(), yc, alpha=0.7, temperature=2.0).backward()
+
+    ms = timed(kd_step)
+    out["cfg3_distillation_step_2x128_bf16"] = {"ms_per_step": ms, "voxels_per_s": vox / ms * 1e3}
+    seg = UNet3DDann(1, CLASSES, dropout_rate=0.0).to(dev).train()
+    disc = DomainDiscriminator(256).to(dev).train()
+    xt = structured_volume(2, PATCH, seed=22)[0].to(dev)
+    dom_labels = torch.tensor([0, 0, 1, 1], device=dev)
+
+    def dann_step(lam=0.2):
+        seg.zero_grad(set_to_none=True); disc.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            o_s, f_s = seg(xc, return_features=True)
+            _, f_t = seg(xt, return_features=True)
+        task = M.combined_ce_tversky_loss(o_s.float(), yc, alpha=0.5, beta=0.5)
+        dom = domain_cross_entropy(torch.cat([disc(grad_reverse(f_s, lam)), disc(grad_reverse(f_t, lam))], 0), dom_labels)
+        (task + lam * dom).backward()
+
+    ms = timed(dann_step)
+    out["cfg4_dann_step_2x128_source_plus_2x128_target_bf16"] = {"ms_per_step": ms, "voxels_per_s": 2 * vox / ms * 1e3}
+    del xc, yc, xt
+    torch.cuda.empty_cache()
+    vol = torch.rand(1, 1, 256, 512, 512, device=dev)
+    lab = torch.randint(0, CLASSES, (1, 1, 256, 512, 512), device=dev)
+    student.eval(); student.compute_dtype = torch.bfloat16
+    with torch.no_grad():
+        ms = timed(lambda: evaluate_volume(student, vol, lab, window=128, stride=128), warm=1, iters=3)
+    out["cfg5_sliding_window_512x512x256_win128_stride128_bf16"] = {"ms_per_volume": ms, "voxels_per_s": vol.numel() / ms * 1e3}
+    return out
+
+
+def gpu_reference_step(dev, x_d, y_d, sd0):
+    """The reference's own arithmetic (oracle restatement: torch ops, cuDNN) under CUDA bf16 autocast on the SAME GPU and batch:
+    the step-0 loss is the value this arm's step-0 loss is asserted against, the time is the 'PyTorch eager + cuDNN' bar."""
+    from oracle import metrics_oracle as OM
+    from oracle.unet_oracle import train_step_grads
+    torch.backends.cudnn.benchmark = True
+    sd = {k: v.to(dev) for k, v in sd0.items()}
+    loss0, _, _, _ = train_step_grads(sd, x_d, y_d, OM.combined_loss, autocast_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); train_step_grads(sd, x_d, y_d, OM.combined_loss, autocast_dtype=torch.bfloat16); e.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(e))
+    return float(loss0), statistics.median(ts)
 
 def run_ours(args):
     import torch.distributed as dist
@@ -210,11 +342,18 @@ def run_ours(args):
 
     torch.manual_seed(0)
     model = UNet3D(in_channels=1, out_channels=CLASSES, dropout_rate=args.dropout).to(dev).train()
-    trainer = DataParallelTrainer(model, M.combined_loss, lr=1e-3, autocast_dtype=torch.bfloat16,
-                                  metrics_fn=lambda lg, y: F.confusion_counts(lg, y))
+    trainer = DataParallelTrainer(model, M.combined_loss, lr=1e-3, autocast_dtype=torch.bfloat16, metrics_fn="confusion")
     x_h, y_h = structured_volume(BATCH_PER_GPU, PATCH, seed=1234 + rank)
+    if args.wire == "bf16u8":
+        # what crosses PCIe: the volume as bf16 (the value the first kernel would round the fp32 volume to anyway) and the class
+        # indices as uint8 — 12.6 MB per step instead of the reference loader's fp32 + int64 = 50.3 MB; identical training values
+        x_h, y_h = x_h.bfloat16(), y_h.to(torch.uint8)
     x_h, y_h = x_h.pin_memory(), y_h.pin_memory()
     x_d, y_d = x_h.to(dev), y_h.to(dev)
+
+    # the very first optimisation step from the initial weights, eagerly: its loss is checked against the oracle below
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()} if rank == 0 else None
+    loss_step0 = float(trainer.step(x_d, y_d).item())
 
     use_graph = not args.no_graph
     launches_per_step = None
@@ -302,16 +441,32 @@ def run_ours(args):
     e2e_value = vox_step * args.steps / e2e_s
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel + CPU baseline (rank 0, N = 1 only for the CPU leg) -----
-    k_ms, k_flops = time_top_conv_kernel(dev)
-    achieved = k_flops / (k_ms / 1e3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "conv3d_tc3_kernel (persistent; decoder.3.c0 fprop, 2x128^3, (16+16)->16 ch, 115.96 GFLOP/launch)", "achieved": achieved,
-                "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"],
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this shape from one `ncu --set full` capture
-                # (profiles/r01_ncu_final_kernels_summary.md): 268.6 MB + 105.6 MB; algorithmic bytes are 268.4 in + 134.2 out
-                "traffic": 374207232, "traffic_unit": "bytes/launch",
-                "peak_source": peaks["source"] + " bf16 burst (kernel timed alone)", "kernel_ms": k_ms,
-                "step_conv_tflops_vs_sustained": (F_TRAIN_PER_VOXEL * vox_step / world / (ms / args.steps / 1e3) / 1e12) / peaks["bf16_sustained"]}
+    # ---- checker: this arm's first step against the reference's arithmetic (oracle under CUDA bf16 autocast, same GPU, same
+    # batch, same initial weights); a mismatch is an error, not a number
+    trainer.graph = None
+    ref_loss0, ref_ms = gpu_reference_step(dev, x_d.float(), y_d.long(), sd0)
+    if not abs(loss_step0 - ref_loss0) <= 1e-2 * abs(ref_loss0):
+        raise SystemExit(f"bench.py: step-0 loss {loss_step0:.6f} does not match the oracle's {ref_loss0:.6f} (bf16 tolerance 1e-2): refusing to report a number")
+    gpu_reference = {"what": "the reference's arithmetic (oracle restatement: torch ops, cuDNN) under CUDA bf16 autocast, eager, fwd + loss + bwd, same GPU / batch / weights",
+                     "ms_per_step": ref_ms, "voxels_per_s": BATCH_PER_GPU * PATCH ** 3 / ref_ms * 1e3, "loss_step0": ref_loss0}
+    # ---- roofline: the dominant kernel first, then every kernel that carries the step, all timed in this run ----------------
+    kernels = time_step_kernels(dev, peaks)
+    top = kernels[0]
+    ncu = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_summary.json")) as f:
+            ncu = json.load(f)
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": top["kernel"] + " (2x128^3, 115.96 GFLOP/launch)", "achieved": top["achieved"],
+                "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": top["frac"],
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this shape from the committed `ncu --set full` capture
+                "traffic": ncu.get("top_kernel_dram_bytes"), "traffic_unit": "bytes/launch",
+                "tensor_pipe_pct": ncu.get("top_kernel_tensor_pipe_pct"), "ncu_source": ncu.get("source"),
+                "peak_source": peaks["source"] + " bf16 burst (kernel timed alone)", "kernel_ms": top["ms"],
+                "step_conv_tflops_vs_sustained": (F_TRAIN_PER_VOXEL * vox_step / world / (ms / args.steps / 1e3) / 1e12) / peaks["bf16_sustained"],
+                "hbm_peak_gbs": peaks["hbm"], "kernels": kernels}
+    extra = time_extra_configs(dev) if (world == 1 and not args.no_extra_configs) else None
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         sec, vox, threads, nsteps = cpu_train_step_sample(PATCH, batch=1)
@@ -324,13 +479,14 @@ def run_ours(args):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "unet3d_train_128cube_b2_per_gpu", "patch": [PATCH] * 3, "batch_per_gpu": BATCH_PER_GPU,
                    "global_batch": BATCH_PER_GPU * world, "classes": CLASSES, "loss": "combined_loss (Dice+CE)", "optimizer": "AdamW (fused, in step)",
-                   "parallelism": f"dp{world}", "cuda_graph": use_graph,
+                   "parallelism": f"dp{world}", "cuda_graph": use_graph, "fused_head": True, "batch_format": args.wire,
                    "l2": "working set per step (>6 GB of activations) far exceeds the 126 MB L2; no explicit flush needed"},
-        "patches_per_s": value / PATCH ** 3, "loss": loss_val,
-        "e2e": {"value": e2e_value, "unit": "voxels/s", "h2d_bytes_per_step": x_h.numel() * 4 + y_h.numel() * 8, "d2h_bytes_per_step": 4,
+        "patches_per_s": value / PATCH ** 3, "loss": loss_val, "loss_step0": loss_step0, "loss_step0_oracle": ref_loss0,
+        "e2e": {"value": e2e_value, "unit": "voxels/s", "h2d_bytes_per_step": x_h.numel() * x_h.element_size() + y_h.numel() * y_h.element_size(),
+                "d2h_bytes_per_step": 4, "wire_format": f"{x_h.dtype} volume + {y_h.dtype} labels, pinned host memory",
                 "ms_per_step": e2e_s / args.steps * 1e3},
         "gpu_launches": (launches_per_step * args.steps) if launches_per_step else eager_launches,
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "gpu_reference": gpu_reference, "extra_configs": extra,
     }
     print(json.dumps(line), flush=True)
 
@@ -343,7 +499,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.0, help="Dropout3d rate (BASELINE config: 0.0; the reference's constructor default is 0.1)")
+    ap.add_argument("--wire", default="bf16u8", choices=["bf16u8", "f32i64"],
+                    help="host batch format of the e2e leg: bf16 volume + uint8 labels (default) or the reference loader's fp32 + int64")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the BASELINE config 3-5 timings (N = 1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -157,6 +157,9 @@ int b200_bn_act_bwd_reduce(int dtype, const void* gy, const void* x, const float
                            int64_t N, int64_t S, int C, float* partials, void* stream);
 /* reduces partials -> dgamma, dbeta (fp32, overwritten) and coefficient vectors for bwd_apply */
 int b200_bn_bwd_finalize(const float* partials, int64_t M, int C, float* dgamma, float* dbeta, float* sums, void* stream);
+/* same over an explicit number of partial rows (b200_head_bwd writes b200_head_blocks() rows) */
+int b200_bn_bwd_finalize_ex(const float* partials, int nblocks, int64_t M, int C, float* dgamma, float* dbeta, float* sums,
+                            void* stream);
 /* dx = scale * (g - [training] (sum_g/M + xhat * sum_gxhat/M)) */
 int b200_bn_act_bwd_apply(int dtype, const void* gy, const void* x, void* dx, const float* scale, const float* shift,
                           const float* mean, const float* invstd, const float* dropmask, int relu,
@@ -186,6 +189,22 @@ int b200_convt2_bwd_weight(int dtype, const void* x, const void* gy, float* dw, 
 /* nearest-neighbour resize of an NDHWC tensor (F.interpolate, models/unet.py:81-83) and its adjoint */
 int b200_nearest_resize_fwd(int dtype, const void* x, void* y, int N, int D, int H, int W, int OD, int OH, int OW, int C, void* stream);
 int b200_nearest_resize_bwd(int dtype, const void* gy, void* gx, int N, int D, int H, int W, int OD, int OH, int OW, int C, void* stream);
+
+/* ---------------------------------------------------------------- fused head (training, bf16, 16 channels, 2..4 classes)
+ * models/unet.py:16-18 (last BatchNorm3d + ReLU), :62,87 (final 1x1x1 conv) and utils/metrics.py:14-40, 65-167 in ONE pass each way.
+ * b200_head_fwd: x = PRE-BatchNorm activation [N*S, 16] bf16; scale/shift/mean from b200_bn_finalize(_ex); target uint8 or int64
+ * (label_bytes 1 / 8); writes fp32 NCDHW logits, the loss sums in b200_kd_loss_fwd's layout (feed b200_seg_loss_finalize) and, when
+ * conf != NULL, the C x C confusion counts conf[target][argmax].  The normalised activation is never materialised.
+ * b200_head_bwd: recomputes it, writes gy = d loss / d (normalised activation) as bf16, the 1x1 conv's dw[C][16] / db[C] and the
+ * BatchNorm-backward partial sums bnpart[b200_head_blocks()][2][16] (finish with b200_bn_bwd_finalize_ex + b200_bn_act_bwd_apply).
+ * Workspaces: wpart b200_head_blocks() * 68 floats, bnpart b200_head_blocks() * 32 floats. */
+int b200_head_blocks(int64_t N, int64_t S);
+int b200_head_fwd(const void* x, const float* scale, const float* shift, const float* mean, const float* w, const float* bias,
+                  int round_bf16, const void* target, int label_bytes, int64_t N, int64_t S, int Cin, int C, float* logits,
+                  double* sums, unsigned long long* conf, void* stream);
+int b200_head_bwd(const float* logits, const void* target, int label_bytes, const float* coef, const float* gout, const void* x,
+                  const float* scale, const float* shift, const float* mean, const float* invstd, const float* w, int64_t N,
+                  int64_t S, int Cin, int C, void* gy, float* wpart, float* bnpart, float* dw, float* db, void* stream);
 
 /* ---------------------------------------------------------------- final 1x1x1 conv  models/unet.py:62,87
  * x NDHWC (dtype) -> logits NCDHW fp32 [N, Cout, S]; w [Cout, Cin] fp32.

@@ -64,6 +64,10 @@ def _declare(lib) -> None:
         "b200_bn_act_fwd": (I, [I, P, P, P, P, P, P, I, L, L, I, P]),
         "b200_bn_act_bwd_reduce": (I, [I, P, P, P, P, P, P, P, I, L, L, I, P, P]),
         "b200_bn_bwd_finalize": (I, [P, L, I, P, P, P, P]),
+        "b200_bn_bwd_finalize_ex": (I, [P, I, L, I, P, P, P, P]),
+        "b200_head_blocks": (I, [L, L]),
+        "b200_head_fwd": (I, [P, P, P, P, P, P, I, P, I, L, L, I, I, P, P, P, P]),
+        "b200_head_bwd": (I, [P, P, I, P, P, P, P, P, P, P, P, L, L, I, I, P, P, P, P, P, P]),
         "b200_bn_act_bwd_apply": (I, [I, P, P, P, P, P, P, P, P, I, P, I, L, L, I, P]),
         "b200_channel_sum": (I, [I, P, L, I, P, P, P]),
         "b200_maxpool2_fwd": (I, [I, P, P, I, I, I, I, I, P]),

@@ -800,6 +800,17 @@ extern "C" int b200_bn_bwd_finalize(const float* partials, int64_t M, int C, flo
   return B200_OK;
 }
 
+// same over an explicit number of partial rows (the fused head's backward writes b200_head_blocks() rows)
+extern "C" int b200_bn_bwd_finalize_ex(const float* partials, int nblocks, int64_t M, int C, float* dgamma, float* dbeta, float* sums,
+                                       void* stream) {
+  int rc = check_rows("bn_bwd_finalize_ex", M, C);
+  if (rc) return rc;
+  B200_REQUIRE(partials && sums && nblocks > 0, B200_ERR_SHAPE, "bn_bwd_finalize_ex: null pointer / no partial rows");
+  bn_bwd_finalize_kernel<<<C, kFinThreads, 0, (cudaStream_t)stream>>>(partials, nblocks, M, C, dgamma, dbeta, sums);
+  B200_CHECK_LAUNCH("bn_bwd_finalize_ex");
+  return B200_OK;
+}
+
 extern "C" int b200_bn_act_bwd_apply(int dtype, const void* gy, const void* x, void* dx, const float* scale,
                                      const float* shift, const float* mean, const float* invstd, const float* dropmask,
                                      int relu, const float* sums, int training, int64_t N, int64_t S, int C, void* stream) {

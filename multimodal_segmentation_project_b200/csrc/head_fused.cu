@@ -1,0 +1,312 @@
+// head_fused.cu — the network's head as two single-pass, HBM-bound kernels (bf16 activations, 16 channels, <= 4 classes).
+//
+// Reference call sites fused here: models/unet.py:16-18 (last BatchNorm3d + ReLU of decoder[-1]), :62,87 (final 1x1x1 conv),
+// utils/metrics.py:14-40 / :137-167 (softmax + CE + Dice / Tversky sums), :65-129 (argmax + per-class counts).
+//
+// Forward: one read of the PRE-BatchNorm activation (32 B / voxel) and of the labels (1 or 8 B), one write of the fp32 NCDHW
+// logits (16 B): the normalised activation is never materialised.  Replaces bn_act_fwd (64 B/voxel) + conv1x1_fwd (48) +
+// seg_loss_fwd (24) + confusion (24).  Backward: reads logits, labels and the pre-BN activation again, recomputes softmax and
+// the normalised activation, and produces in one pass the loss gradient, the 1x1 conv's weight / bias gradient partials, the
+// gradient w.r.t. the normalised activation (bf16, 32 B written) and the two BatchNorm-backward channel sums.  Replaces
+// seg_loss_bwd (40) + conv1x1_bwd (80) + bn_act_bwd_reduce (64).
+// Arithmetic is the unfused kernels' arithmetic (same rounding points: BN output and gx rounded to bf16, logits optionally
+// rounded to bf16), so that logits and confusion counts are bit-identical to the unfused path.
+#include "common.cuh"
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+constexpr int kThreads = 256;
+constexpr int CIN = 16;
+constexpr int CMAX = 4;
+constexpr int kMaxBlocks = 2 * B200_NUM_SMS;     // backward: 2 resident CTAs per SM, one wave
+
+__device__ __forceinline__ bool better(float cand, float best) { return (cand > best) || ((cand != cand) && (best == best)); }
+
+struct Softmax4 {
+  float p[CMAX];
+  float lse;
+  __device__ __forceinline__ void compute(const float (&z)[CMAX], int C) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) m = fmaxf(m, z[c]);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) { p[c] = expf(z[c] - m); s += p[c]; }
+    const float inv = 1.f / s;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) p[c] *= inv;
+    lse = m + logf(s);
+  }
+};
+
+// y = relu(bf16(fma(x - mean, scale, shift))) for the 16 channels of one voxel; returns the values as fp32
+__device__ __forceinline__ void bn_relu16(const uint4 (&raw)[2], const float* __restrict__ sc, const float* __restrict__ sh,
+                                          const float* __restrict__ mu, float (&xc)[CIN], float (&y)[CIN]) {
+  const uint32_t w[8] = {raw[0].x, raw[0].y, raw[0].z, raw[0].w, raw[1].x, raw[1].y, raw[1].z, raw[1].w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xffff0000u);
+    xc[2 * i] = lo - mu[2 * i];
+    xc[2 * i + 1] = hi - mu[2 * i + 1];
+  }
+#pragma unroll
+  for (int k = 0; k < CIN; ++k) {
+    const float t = __bfloat162float(__float2bfloat16_rn(fmaf(xc[k], sc[k], sh[k])));
+    y[k] = fmaxf(t, 0.f);
+  }
+}
+
+// sums layout = seg_loss_fwd's (loss_kernels.cu): [0] CE sum, per class k: [4+4k] I, [5+4k] P, [6+4k] T
+template <typename LabelT>
+__global__ void __launch_bounds__(kThreads)
+head_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                const float* __restrict__ w, const float* __restrict__ bias, int round_bf16, const LabelT* __restrict__ target, int64_t N,
+                int64_t S, int C, float* __restrict__ logits, double* __restrict__ sums, unsigned long long* __restrict__ conf) {
+  __shared__ float ws[CMAX * CIN + CMAX + 3 * CIN];
+  __shared__ unsigned int hist[kThreads / 32][CMAX * CMAX];
+  __shared__ float red[kThreads / 32][1 + 3 * CMAX];
+  float* bs = ws + CMAX * CIN;
+  float* sc = bs + CMAX; float* sh = sc + CIN; float* mu = sh + CIN;
+  for (int i = threadIdx.x; i < CMAX * CIN; i += blockDim.x) ws[i] = i < C * CIN ? w[i] : 0.f;
+  if (threadIdx.x < CMAX) bs[threadIdx.x] = (bias && threadIdx.x < C) ? bias[threadIdx.x] : 0.f;
+  if (threadIdx.x < CIN) { sc[threadIdx.x] = scale[threadIdx.x]; sh[threadIdx.x] = shift[threadIdx.x]; mu[threadIdx.x] = mean[threadIdx.x]; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < CMAX * CMAX) hist[warp][lane] = 0;
+  __syncthreads();
+
+  float ce = 0.f, accI[CMAX], accP[CMAX], accT[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) accI[c] = accP[c] = accT[c] = 0.f;
+  const int64_t total = N * S, stride = (int64_t)gridDim.x * blockDim.x;
+  // every lane of a warp runs the same number of iterations (match_any below needs the full mask)
+  for (int64_t vb = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); vb < total; vb += stride) {
+    const int64_t v = vb + lane;
+    const bool active = v < total;
+    int key = -1;
+    if (active) {
+      uint4 raw[2];
+      raw[0] = __ldcs(reinterpret_cast<const uint4*>(x + v * CIN));
+      raw[1] = __ldcs(reinterpret_cast<const uint4*>(x + v * CIN) + 1);
+      const long long yy = (long long)target[v];
+      float xc[CIN], y[CIN], z[CMAX];
+      bn_relu16(raw, sc, sh, mu, xc, y);
+#pragma unroll
+      for (int co = 0; co < CMAX; ++co) {
+        float a = bs[co];
+#pragma unroll
+        for (int k = 0; k < CIN; ++k) a = fmaf(y[k], ws[co * CIN + k], a);
+        z[co] = round_bf16 ? __bfloat162float(__float2bfloat16_rn(a)) : a;
+      }
+      const int64_t n = v / S, sp = v - n * S;
+#pragma unroll
+      for (int co = 0; co < CMAX; ++co)
+        if (co < C) logits[(n * C + co) * S + sp] = z[co];
+      Softmax4 sm;
+      sm.compute(z, C);
+      float zy = 0.f;
+      float best = z[0];
+      int arg = 0;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) {
+          accP[c] += sm.p[c];
+          if (c == yy) { accI[c] += sm.p[c]; accT[c] += 1.f; zy = z[c]; }
+          if (c > 0 && better(z[c], best)) { best = z[c]; arg = c; }
+        }
+      ce += sm.lse - zy;
+      key = (yy >= 0 && yy < C) ? (int)yy * C + arg : -1;
+    }
+    if (conf) {
+      const unsigned peers = __match_any_sync(0xffffffffu, key);
+      if (key >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(&hist[warp][key], (unsigned)__popc(peers));
+    }
+  }
+  ce = warp_sum(ce);
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) { accI[c] = warp_sum(accI[c]); accP[c] = warp_sum(accP[c]); accT[c] = warp_sum(accT[c]); }
+  if (lane == 0) {
+    red[warp][0] = ce;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) { red[warp][1 + 3 * c] = accI[c]; red[warp][2 + 3 * c] = accP[c]; red[warp][3 + 3 * c] = accT[c]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 1 + 3 * CMAX) {
+    double t = 0.0;
+    for (int wq = 0; wq < kThreads / 32; ++wq) t += (double)red[wq][threadIdx.x];
+    const int q = threadIdx.x;
+    if (q == 0) atomicAdd(&sums[0], t);
+    else {
+      const int c = (q - 1) / 3, f = (q - 1) % 3;
+      if (c < C) atomicAdd(&sums[4 + 4 * c + f], t);
+    }
+  }
+  if (conf && threadIdx.x < C * C) {
+    unsigned long long t = 0;
+    for (int wq = 0; wq < kThreads / 32; ++wq) t += hist[wq][threadIdx.x];
+    if (t) atomicAdd(&conf[threadIdx.x], t);
+  }
+}
+
+// coef layout = seg_loss_finalize's: [0] w_ce / Nvox, [1] kd (unused here), [2 + c] a_c, [2 + C + c] b_c
+// wpart[block][CMAX * (CIN + 1)] = partial dW (co, ci) and db (co, CIN); bnpart[block][2][CIN] = partial (sum g, invstd * sum g * (x - mean))
+template <typename LabelT>
+__global__ void __launch_bounds__(kThreads, 2)
+head_bwd_kernel(const float* __restrict__ logits, const LabelT* __restrict__ target, const float* __restrict__ coef, const float* __restrict__ gout,
+                const bf16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                const float* __restrict__ invstd, const float* __restrict__ w, int64_t N, int64_t S, int C, bf16* __restrict__ gy,
+                float* __restrict__ wpart, float* __restrict__ bnpart) {
+  constexpr int P = CMAX * (CIN + 1);
+  __shared__ float ws[CMAX * CIN + 3 * CIN];
+  __shared__ float red[kThreads / 32][P + 2 * CIN];
+  float* sc = ws + CMAX * CIN; float* sh = sc + CIN; float* mu = sh + CIN;
+  for (int i = threadIdx.x; i < CMAX * CIN; i += blockDim.x) ws[i] = i < C * CIN ? w[i] : 0.f;
+  if (threadIdx.x < CIN) { sc[threadIdx.x] = scale[threadIdx.x]; sh[threadIdx.x] = shift[threadIdx.x]; mu[threadIdx.x] = mean[threadIdx.x]; }
+  __syncthreads();
+  const float go = gout[0];
+  const float w_ce = coef[0] * go;
+  float ca[CMAX], cb[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) { ca[c] = c < C ? coef[2 + c] * go : 0.f; cb[c] = c < C ? coef[2 + C + c] * go : 0.f; }
+  float dw[CMAX][CIN], db[CMAX], a0[CIN], a1[CIN];
+#pragma unroll
+  for (int co = 0; co < CMAX; ++co) {
+    db[co] = 0.f;
+#pragma unroll
+    for (int k = 0; k < CIN; ++k) dw[co][k] = 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < CIN; ++k) a0[k] = a1[k] = 0.f;
+
+  const int64_t total = N * S, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += stride) {
+    const int64_t n = v / S, sp = v - n * S;
+    float z[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) z[c] = c < C ? __ldcs(logits + (n * C + c) * S + sp) : 0.f;
+    uint4 raw[2];
+    raw[0] = __ldcs(reinterpret_cast<const uint4*>(x + v * CIN));
+    raw[1] = __ldcs(reinterpret_cast<const uint4*>(x + v * CIN) + 1);
+    const int yy = (int)target[v];
+    Softmax4 sm;
+    sm.compute(z, C);
+    float wv[CMAX], pw = 0.f, dz[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) { wv[c] = (c == yy ? ca[c] : 0.f) + cb[c]; pw += sm.p[c] * wv[c]; }
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) dz[c] = c < C ? w_ce * (sm.p[c] - (c == yy ? 1.f : 0.f)) + sm.p[c] * (wv[c] - pw) : 0.f;
+    float xc[CIN], y[CIN];
+    bn_relu16(raw, sc, sh, mu, xc, y);
+    uint32_t packed[8];
+    float g[CIN];
+#pragma unroll
+    for (int k = 0; k < CIN; ++k) {
+      float a = 0.f;
+#pragma unroll
+      for (int co = 0; co < CMAX; ++co) a = fmaf(dz[co], ws[co * CIN + k], a);
+      const bf16 r = __float2bfloat16_rn(a);                 // gradient w.r.t. the normalised activation, stored as bf16
+      g[k] = y[k] > 0.f ? __bfloat162float(r) : 0.f;         // ... and through the ReLU (y > 0 <=> pre-activation > 0)
+      if (k & 1) packed[k >> 1] |= (uint32_t)__bfloat16_as_ushort(r) << 16; else packed[k >> 1] = (uint32_t)__bfloat16_as_ushort(r);
+      a0[k] += g[k];
+      a1[k] = fmaf(g[k], xc[k], a1[k]);
+    }
+    reinterpret_cast<uint4*>(gy + v * CIN)[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    reinterpret_cast<uint4*>(gy + v * CIN)[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+#pragma unroll
+    for (int co = 0; co < CMAX; ++co) {
+      db[co] += dz[co];
+#pragma unroll
+      for (int k = 0; k < CIN; ++k) dw[co][k] = fmaf(dz[co], y[k], dw[co][k]);
+    }
+  }
+  // fixed-shape fold: warp butterflies, then the warps in order
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int co = 0; co < CMAX; ++co) {
+#pragma unroll
+    for (int k = 0; k < CIN; ++k) {
+      const float t = warp_sum(dw[co][k]);
+      if (lane == 0) red[warp][co * (CIN + 1) + k] = t;
+    }
+    const float t = warp_sum(db[co]);
+    if (lane == 0) red[warp][co * (CIN + 1) + CIN] = t;
+  }
+#pragma unroll
+  for (int k = 0; k < CIN; ++k) {
+    const float t0 = warp_sum(a0[k]), t1 = warp_sum(a1[k]);
+    if (lane == 0) { red[warp][P + k] = t0; red[warp][P + CIN + k] = t1; }
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < P + 2 * CIN; q += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < kThreads / 32; ++wq) t += red[wq][q];
+    if (q < P) wpart[(int64_t)blockIdx.x * P + q] = t;
+    else if (q < P + CIN) bnpart[(int64_t)blockIdx.x * 2 * CIN + (q - P)] = t;
+    else bnpart[(int64_t)blockIdx.x * 2 * CIN + CIN + (q - P - CIN)] = t * invstd[q - P - CIN];
+  }
+}
+
+// dW / db: fold wpart over the blocks in fixed order (fp64)
+__global__ void head_bwd_finalize_kernel(const float* __restrict__ wpart, int nblocks, int C, float* __restrict__ dw, float* __restrict__ db) {
+  constexpr int P = CMAX * (CIN + 1);
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= P) return;
+  double t = 0.0;
+  for (int b = 0; b < nblocks; ++b) t += (double)wpart[(int64_t)b * P + q];
+  const int co = q / (CIN + 1), k = q % (CIN + 1);
+  if (co >= C) return;
+  if (k < CIN) dw[co * CIN + k] = (float)t;
+  else if (db) db[co] = (float)t;
+}
+
+}  // namespace
+
+extern "C" int b200_head_blocks(int64_t N, int64_t S) { return b200_grid_for(N * S, kThreads, kMaxBlocks); }
+
+extern "C" int b200_head_fwd(const void* x, const float* scale, const float* shift, const float* mean, const float* w, const float* bias,
+                             int round_bf16, const void* target, int label_bytes, int64_t N, int64_t S, int Cin, int C, float* logits,
+                             double* sums, unsigned long long* conf, void* stream) {
+  B200_REQUIRE(x && scale && shift && mean && w && target && logits && sums, B200_ERR_SHAPE, "head_fwd: null pointer");
+  B200_REQUIRE(Cin == CIN && C >= 2 && C <= CMAX, B200_ERR_UNSUPPORTED, "head_fwd: serves %d input channels and 2..%d classes (got %d, %d)", CIN, CMAX, Cin, C);
+  B200_REQUIRE(label_bytes == 1 || label_bytes == 8, B200_ERR_UNSUPPORTED, "head_fwd: labels must be uint8 or int64");
+  B200_REQUIRE(b200_aligned(x, 16), B200_ERR_ALIGN, "head_fwd: activation must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * (4 + 4 * C), st));
+  if (conf) B200_CUDA(cudaMemsetAsync(conf, 0, sizeof(unsigned long long) * C * C, st));
+  const int grid = b200_grid_for(N * S, kThreads, B200_NUM_SMS * 8);
+  if (label_bytes == 1)
+    head_fwd_kernel<uint8_t><<<grid, kThreads, 0, st>>>((const bf16*)x, scale, shift, mean, w, bias, round_bf16, (const uint8_t*)target, N, S, C, logits, sums, conf);
+  else
+    head_fwd_kernel<int64_t><<<grid, kThreads, 0, st>>>((const bf16*)x, scale, shift, mean, w, bias, round_bf16, (const int64_t*)target, N, S, C, logits, sums, conf);
+  B200_CHECK_LAUNCH("head_fwd");
+  return B200_OK;
+}
+
+// wpart: b200_head_blocks() * 4 * 17 floats, bnpart: b200_head_blocks() * 2 * 16 floats.  Afterwards dw[C][16], db[C] hold the 1x1 conv's
+// gradients; bnpart goes to b200_bn_bwd_finalize_ex(bnpart, b200_head_blocks(), ...) and gy to b200_bn_act_bwd_apply.
+extern "C" int b200_head_bwd(const float* logits, const void* target, int label_bytes, const float* coef, const float* gout, const void* x,
+                             const float* scale, const float* shift, const float* mean, const float* invstd, const float* w, int64_t N,
+                             int64_t S, int Cin, int C, void* gy, float* wpart, float* bnpart, float* dw, float* db, void* stream) {
+  B200_REQUIRE(logits && target && coef && gout && x && scale && shift && mean && invstd && w && gy && wpart && bnpart && dw, B200_ERR_SHAPE,
+               "head_bwd: null pointer");
+  B200_REQUIRE(Cin == CIN && C >= 2 && C <= CMAX, B200_ERR_UNSUPPORTED, "head_bwd: serves %d input channels and 2..%d classes (got %d, %d)", CIN, CMAX, Cin, C);
+  B200_REQUIRE(label_bytes == 1 || label_bytes == 8, B200_ERR_UNSUPPORTED, "head_bwd: labels must be uint8 or int64");
+  B200_REQUIRE(b200_aligned(x, 16) && b200_aligned(gy, 16), B200_ERR_ALIGN, "head_bwd: activations must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = b200_head_blocks(N, S);
+  if (label_bytes == 1)
+    head_bwd_kernel<uint8_t><<<grid, kThreads, 0, st>>>(logits, (const uint8_t*)target, coef, gout, (const bf16*)x, scale, shift, mean, invstd, w, N, S, C,
+                                                        (bf16*)gy, wpart, bnpart);
+  else
+    head_bwd_kernel<int64_t><<<grid, kThreads, 0, st>>>(logits, (const int64_t*)target, coef, gout, (const bf16*)x, scale, shift, mean, invstd, w, N, S, C,
+                                                        (bf16*)gy, wpart, bnpart);
+  B200_CHECK_LAUNCH("head_bwd");
+  head_bwd_finalize_kernel<<<1, 128, 0, st>>>(wpart, grid, C, dw, db);
+  B200_CHECK_LAUNCH("head_bwd_finalize");
+  return B200_OK;
+}

@@ -116,8 +116,11 @@ class DataParallelTrainer:
 
     def __init__(self, model, loss_fn: Callable, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
                  autocast_dtype: Optional[torch.dtype] = torch.bfloat16, process_group=None, overlap=True,
-                 metrics_fn: Optional[Callable] = None, optimizer_factory=None, accumulation_steps: int = 1):
+                 metrics_fn: Optional[Callable] = None, optimizer_factory=None, accumulation_steps: int = 1, fused_head: bool = True):
+        # metrics_fn: a callable (logits, target) -> anything, or the string "confusion" = int64 [C, C] counts conf[target, argmax]
+        # (computed inside the fused head when the model offers it: UNet3D.forward_with_loss)
         self.model, self.loss_fn, self.metrics_fn = model, loss_fn, metrics_fn
+        self.fused_head = fused_head and os.environ.get("B200_FUSED_HEAD", "1") != "0"
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.autocast_dtype = autocast_dtype
@@ -219,13 +222,24 @@ class DataParallelTrainer:
 
     def _step_body(self, x, y):
         self.fp.detach_grads()
-        if self.autocast_dtype is not None and x.is_cuda:
-            with torch.autocast("cuda", dtype=self.autocast_dtype):
-                out = self.model(x)
+        want_conf = isinstance(self.metrics_fn, str) and self.metrics_fn == "confusion"
+        fwl = getattr(self.model, "forward_with_loss", None) if self.fused_head else None
+        conf = None
+        if fwl is not None and getattr(self.loss_fn, "_b200_spec", None) is not None:
+            # model + loss (+ confusion counts) through one call: the head runs fused when the configuration allows
+            if self.autocast_dtype is not None and x.is_cuda:
+                with torch.autocast("cuda", dtype=self.autocast_dtype):
+                    logits, loss, conf = fwl(x, y, self.loss_fn, want_confusion=want_conf)
+            else:
+                logits, loss, conf = fwl(x, y, self.loss_fn, want_confusion=want_conf)
         else:
-            out = self.model(x)
-        logits = out[0] if isinstance(out, tuple) else out
-        loss = self.loss_fn(logits.float(), y)
+            if self.autocast_dtype is not None and x.is_cuda:
+                with torch.autocast("cuda", dtype=self.autocast_dtype):
+                    out = self.model(x)
+            else:
+                out = self.model(x)
+            logits = out[0] if isinstance(out, tuple) else out
+            loss = self.loss_fn(logits.float(), y if y.dtype == torch.int64 else y.long())
         if self.accum == 1:
             loss.backward()
             self.allreduce_grads()
@@ -240,7 +254,13 @@ class DataParallelTrainer:
                     for t in self.fp.buckets():
                         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
                 self.opt.step(grad_scale=1.0 / self.world)
-        metrics = self.metrics_fn(logits.detach(), y) if self.metrics_fn is not None else None
+        if want_conf:
+            if conf is None:
+                from .functional import confusion_counts
+                conf = confusion_counts(logits.detach(), y if y.dtype == torch.int64 else y.long())
+            metrics = conf
+        else:
+            metrics = self.metrics_fn(logits.detach(), y) if self.metrics_fn is not None else None
         return loss.detach(), metrics
 
     def step(self, x, y):

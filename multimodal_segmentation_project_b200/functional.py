@@ -55,6 +55,9 @@ def to_channels_last(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """NCDHW fp32 -> NDHWC ``dtype``."""
     _require_cuda(x)
     L = _lib.load()
+    if x.dtype == torch.bfloat16 and dtype == torch.bfloat16 and x.shape[1] == 1:
+        # a bf16 single-channel volume already IS the channels-last bf16 tensor (e.g. batches shipped over PCIe as bf16)
+        return x.detach().contiguous().reshape(x.shape[0], *x.shape[2:], 1)
     x = x.detach().float().contiguous()
     N, C = x.shape[0], x.shape[1]
     sp = tuple(x.shape[2:])
@@ -330,32 +333,177 @@ class _ConvBNAct(torch.autograd.Function):
                                     _ptr(stats[3]), _ptr(dropmask), 1, _ptr(sums), int(ctx.training), N, S, Cout, _stream()),
             "bn_act_bwd_apply",
         )
-        dw = db = None
-        need_w = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
-        need_x = ctx.needs_input_grad[0] or (x1 is not None and ctx.needs_input_grad[1])
-        side = keep = None
-        if need_w:
-            # A conv bias feeding a batch-statistics BatchNorm has an exactly-zero gradient (the mean subtraction
-            # cancels it; the reference computes round-off noise around 0): skip the column-sum pass.
-            side = fork_side(dev) if need_x else None
-            if side is None:
-                dw, db = conv3d_wgrad_raw(x0, x1, dconv, want_bias=not ctx.training)
-            else:
-                dw, db, keep = conv3d_wgrad_raw(x0, x1, dconv, want_bias=not ctx.training, side=side)
-            if db is None:
-                db = torch.zeros(Cout, dtype=torch.float32, device=dev)
-            if not ctx.has_bias:
-                db = None
-        dx0 = dx1 = None
-        if need_x:
-            c0 = x0.shape[-1]
-            c1 = 0 if x1 is None else x1.shape[-1]
-            impl = conv3d_select_impl(dconv, None, c0, c1, ctx.impl_req)
-            wpack = pack_conv3_weights(weight, pack_mode(impl, True), conv_out.dtype)
-            dx0, dx1 = conv3d_k3_raw(dconv, None, wpack, None, c0, c1, impl)
-        join_side(side, dev, x0, x1, dconv, keep)
-        del keep
+        dx0, dx1, dw, db = _conv_bwd_from_dconv(ctx, x0, x1, weight, dconv, zero_bias_grad=ctx.training)
         return (dx0, dx1, dw, db, dgamma, dbeta, None, None, None, None, None, None, None, None)
+
+
+def _conv_bwd_from_dconv(ctx, x0, x1, weight, dconv, zero_bias_grad):
+    """Weight / bias / data gradients of the 3x3x3 convolution given d loss / d conv_out (shared by _ConvBNAct and _ConvStats).
+    zero_bias_grad: the bias feeds a batch-statistics BatchNorm, its gradient is exactly zero."""
+    dev = dconv.device
+    Cout = dconv.shape[-1]
+    dw = db = None
+    need_w = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+    need_x = ctx.needs_input_grad[0] or (x1 is not None and ctx.needs_input_grad[1])
+    side = keep = None
+    if need_w:
+        side = fork_side(dev) if need_x else None
+        if side is None:
+            dw, db = conv3d_wgrad_raw(x0, x1, dconv, want_bias=not zero_bias_grad)
+        else:
+            dw, db, keep = conv3d_wgrad_raw(x0, x1, dconv, want_bias=not zero_bias_grad, side=side)
+        if db is None:
+            db = torch.zeros(Cout, dtype=torch.float32, device=dev)
+        if not ctx.has_bias:
+            db = None
+    dx0 = dx1 = None
+    if need_x:
+        c0 = x0.shape[-1]
+        c1 = 0 if x1 is None else x1.shape[-1]
+        impl = conv3d_select_impl(dconv, None, c0, c1, ctx.impl_req)
+        wpack = pack_conv3_weights(weight, pack_mode(impl, True), dconv.dtype)
+        dx0, dx1 = conv3d_k3_raw(dconv, None, wpack, None, c0, c1, impl)
+    join_side(side, dev, x0, x1, dconv, keep)
+    del keep
+    return dx0, dx1, dw, db
+
+
+def _conv_and_batch_stats(L, x0, x1, weight, bias, gamma, beta, running_mean, running_var, nbt, eps, momentum, impl):
+    """conv3x3x3 + training-mode BatchNorm statistics (fused into the conv epilogue where a kernel offers it) + finalize.
+    Returns (conv_out, stats[4, C] = scale, shift, mean, invstd)."""
+    N, D, H, W, _ = x0.shape
+    Cout = weight.shape[0]
+    dev = x0.device
+    M = N * D * H * W
+    wpack = pack_conv3_weights(weight, pack_mode(impl, False), x0.dtype)
+    stats = torch.empty((4, Cout), dtype=torch.float32, device=dev)
+    g32, b32, bias32 = _f32(gamma), _f32(beta), _f32(bias)
+    c0, c1 = x0.shape[-1], (0 if x1 is None else x1.shape[-1])
+    rows = L.b200_conv3d_k3_bnstats_blocks(_dt(x0), impl, c0, c1, Cout, 0, N, D, H, W) if _fuse_bn_stats else 0
+    partials = _bn_partials(Cout, dev)
+    if rows > 0:
+        conv_out = torch.empty((N, D, H, W, Cout), dtype=x0.dtype, device=dev)
+        check(L.b200_conv3d_k3_bnstats(_dt(x0), impl, _ptr(x0), c0, _ptr(x1), c1, _ptr(wpack), _ptr(bias32), _ptr(conv_out), Cout,
+                                       N, D, H, W, _ptr(partials), _stream()), "conv3d_k3_bnstats")
+        check(L.b200_bn_finalize_ex(_ptr(partials), rows, _ptr(bias32), M, Cout, _ptr(g32), _ptr(b32), float(eps), float(momentum),
+                                    _ptr(running_mean), _ptr(running_var), _ptr(nbt), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]),
+                                    _ptr(stats[3]), _stream()), "bn_finalize_ex")
+    else:
+        conv_out, _ = conv3d_k3_raw(x0, x1, wpack, bias32, Cout, 0, impl)
+        check(L.b200_bn_stats(_dt(conv_out), _ptr(conv_out), M, Cout, _ptr(partials), _stream()), "bn_stats")
+        check(L.b200_bn_finalize(_dt(conv_out), _ptr(conv_out), _ptr(partials), M, Cout, _ptr(g32), _ptr(b32), float(eps), float(momentum), 1,
+                                 _ptr(running_mean), _ptr(running_var), _ptr(nbt), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]),
+                                 _ptr(stats[3]), _stream()), "bn_finalize")
+    return conv_out, stats
+
+
+class _ConvStats(torch.autograd.Function):
+    """Conv3d(k3,p1)+bias and the batch statistics of the BatchNorm3d that follows (models/unet.py:15-16), WITHOUT applying it:
+    the fused head (_FusedHead) normalises on the fly.  Returns (conv_out, stats); the gradient arrives w.r.t. conv_out."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, weight, bias, gamma, beta, running_mean, running_var, nbt, eps, momentum, impl):
+        _require_cuda(x0, x1, weight)
+        L = _lib.load()
+        ctx.impl_req = impl
+        x0 = x0.contiguous()
+        x1 = None if x1 is None else x1.contiguous()
+        impl = conv3d_select_impl(x0, x1, weight.shape[0], 0, impl)
+        conv_out, stats = _conv_and_batch_stats(L, x0, x1, weight, bias, gamma.detach(), beta.detach(), running_mean, running_var, nbt, eps,
+                                                momentum, impl)
+        ctx.save_for_backward(x0, x1, weight)
+        ctx.has_bias = bias is not None
+        ctx.mark_non_differentiable(stats)
+        return conv_out, stats
+
+    @staticmethod
+    def backward(ctx, dconv, _gstats):
+        x0, x1, weight = ctx.saved_tensors
+        dx0, dx1, dw, db = _conv_bwd_from_dconv(ctx, x0, x1, weight, dconv.contiguous(), zero_bias_grad=True)
+        return (dx0, dx1, dw, db, None, None, None, None, None, None, None, None)
+
+
+class _FusedHead(torch.autograd.Function):
+    """Last BatchNorm3d + ReLU, final 1x1x1 conv, segmentation loss and confusion counts in one pass each way
+    (models/unet.py:16-18, 62, 87; utils/metrics.py:14-40, 65-167) — csrc/head_fused.cu."""
+
+    @staticmethod
+    def forward(ctx, conv_out, stats, gamma, beta, fw, fb, target, mode, alpha, beta_t, want_conf, round_bf16):
+        _require_cuda(conv_out, target)
+        L = _lib.load()
+        N, D, H, W, Cin = conv_out.shape
+        C = fw.shape[0]
+        S = D * H * W
+        if target.dtype not in (torch.int64, torch.uint8):
+            raise RuntimeError(f"expected int64 (or uint8) class-index target, got {target.dtype}")
+        if target.numel() != N * S:
+            raise ValueError(f"target shape {tuple(target.shape)} does not match the volume {(N, D, H, W)}")
+        y = target.detach().contiguous()
+        lb = 1 if y.dtype == torch.uint8 else 8
+        dev = conv_out.device
+        w32, b32 = _f32(fw).reshape(C, Cin), _f32(fb)
+        logits = torch.empty((N, C, D, H, W), dtype=torch.float32, device=dev)
+        sums = torch.empty(4 + 4 * C, dtype=torch.float64, device=dev)
+        conf = torch.empty((C, C), dtype=torch.int64, device=dev) if want_conf else None
+        check(L.b200_head_fwd(_ptr(conv_out), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]), _ptr(w32), _ptr(b32), int(round_bf16), _ptr(y), lb,
+                              N, S, Cin, C, _ptr(logits), _ptr(sums), _ptr(conf), _stream()), "head_fwd")
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        coef = torch.empty(2 + 2 * C, dtype=torch.float32, device=dev)
+        check(L.b200_seg_loss_finalize(_ptr(sums), mode, float(alpha), float(beta_t), 1.0, 1.0, 0, N, C, S, _ptr(loss), _ptr(coef), _stream()),
+              "seg_loss_finalize")
+        ctx.save_for_backward(conv_out, stats, w32, logits, y, coef)
+        ctx.fw_shape = tuple(fw.shape)
+        ctx.has_fb = fb is not None
+        ctx.label_bytes = lb
+        ctx.mark_non_differentiable(logits)
+        if conf is not None:
+            ctx.mark_non_differentiable(conf)
+        return loss, logits, conf
+
+    @staticmethod
+    def backward(ctx, gloss, _glogits, _gconf):
+        L = _lib.load()
+        conv_out, stats, w32, logits, y, coef = ctx.saved_tensors
+        N, D, H, W, Cin = conv_out.shape
+        C = w32.shape[0]
+        S = D * H * W
+        dev = conv_out.device
+        go = gloss.detach().float().contiguous().reshape(1)
+        nb = L.b200_head_blocks(N, S)
+        gy = torch.empty_like(conv_out)
+        wpart = torch.empty(nb * 4 * (Cin + 1), dtype=torch.float32, device=dev)
+        bnpart = torch.empty(nb * 2 * Cin, dtype=torch.float32, device=dev)
+        dw = torch.empty((C, Cin), dtype=torch.float32, device=dev)
+        db = torch.empty(C, dtype=torch.float32, device=dev)
+        check(L.b200_head_bwd(_ptr(logits), _ptr(y), ctx.label_bytes, _ptr(coef), _ptr(go), _ptr(conv_out), _ptr(stats[0]), _ptr(stats[1]),
+                              _ptr(stats[2]), _ptr(stats[3]), _ptr(w32), N, S, Cin, C, _ptr(gy), _ptr(wpart), _ptr(bnpart), _ptr(dw), _ptr(db),
+                              _stream()), "head_bwd")
+        dgamma = torch.empty(Cin, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(Cin, dtype=torch.float32, device=dev)
+        sums = torch.empty(2 * Cin, dtype=torch.float32, device=dev)
+        check(L.b200_bn_bwd_finalize_ex(_ptr(bnpart), nb, N * S, Cin, _ptr(dgamma), _ptr(dbeta), _ptr(sums), _stream()), "bn_bwd_finalize_ex")
+        dconv = torch.empty_like(conv_out)
+        check(L.b200_bn_act_bwd_apply(_dt(conv_out), _ptr(gy), _ptr(conv_out), _ptr(dconv), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]),
+                                      _ptr(stats[3]), None, 1, _ptr(sums), 1, N, S, Cin, _stream()), "bn_act_bwd_apply")
+        return (dconv, None, dgamma, dbeta, dw.reshape(ctx.fw_shape), (db if ctx.has_fb else None), None, None, None, None, None, None)
+
+
+def conv_batch_stats(x0, x1, conv, bn, impl=0):
+    """(conv_out, stats) of conv -> BatchNorm3d in training mode, the normalisation itself left to fused_head()."""
+    if bn.momentum is None:
+        raise ValueError("BatchNorm3d(momentum=None) (cumulative moving average) is not supported by libb200unet")
+    for name, buf, want in (("running_mean", bn.running_mean, torch.float32), ("running_var", bn.running_var, torch.float32),
+                            ("num_batches_tracked", bn.num_batches_tracked, torch.int64)):
+        if buf is not None and (buf.dtype != want or not buf.is_contiguous() or not buf.is_cuda):
+            raise TypeError(f"BatchNorm3d.{name} must be a contiguous CUDA {want} tensor (got {buf.dtype} on {buf.device})")
+    return _ConvStats.apply(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                            bn.eps, bn.momentum, impl)
+
+
+def fused_head(conv_out, stats, bn, final_conv, target, mode, alpha=0.5, beta=0.5, want_confusion=False, round_bf16=True):
+    """(loss, logits NCDHW fp32, confusion int64 [C, C] or None)"""
+    return _FusedHead.apply(conv_out, stats, bn.weight, bn.bias, final_conv.weight, final_conv.bias, target, mode, alpha, beta,
+                            want_confusion, round_bf16)
 
 
 def conv_bn_act(x0, x1, conv, bn, dropmask, training, impl=0):

@@ -47,12 +47,16 @@ class DoubleConv(nn.Module):
             return torch.zeros((n, c), dtype=torch.float32, device=device)
         return torch.empty((n, c), dtype=torch.float32, device=device).bernoulli_(1.0 - p).div_(1.0 - p)
 
-    def forward_cl(self, x0, x1=None, impl=0):
-        """Channels-last forward; ``x1`` is the second half of a virtual concat (skip first)."""
+    def forward_cl(self, x0, x1=None, impl=0, defer_last_norm=False):
+        """Channels-last forward; ``x1`` is the second half of a virtual concat (skip first).
+        ``defer_last_norm``: stop after the second convolution and its batch statistics and return ``(conv_out, stats)`` — the
+        caller (the fused head) applies BatchNorm + ReLU on the fly instead of materialising them."""
         seq = self.double_conv
         n = x0.shape[0]
         m0 = self._mask(seq[3], n, seq[0].out_channels, x0.device)
         h = F.conv_bn_act(x0, x1, seq[0], seq[1], m0, seq[1].training, impl)
+        if defer_last_norm:
+            return F.conv_batch_stats(h, None, seq[4], seq[5], impl)
         m1 = self._mask(seq[7], n, seq[4].out_channels, x0.device)
         return F.conv_bn_act(h, None, seq[4], seq[5], m1, seq[5].training, impl)
 
@@ -120,7 +124,7 @@ class UNet3D(nn.Module):
         self.conv_impl = 0         # 0 auto, 1 CUDA-core implicit GEMM, 2 tcgen05
 
     # -- the network body on channels-last tensors; returns (logits NCDHW fp32, bottleneck NDHWC)
-    def _body(self, x):
+    def _body(self, x, head=None):
         if not x.is_cuda:
             raise RuntimeError("UNet3D (b200) needs a CUDA tensor: there is no CPU fallback "
                                "(use the reference implementation or the oracle for CPU runs)")
@@ -143,6 +147,14 @@ class UNet3D(nn.Module):
             skip = skips[idx]
             if h.shape[1:4] != skip.shape[1:4]:
                 h = F.nearest_resize(h, skip.shape[1:4])  # models/unet.py:81-83
+            if head is not None and idx == len(self.upconvs) - 1:
+                # fused head: the last BatchNorm + ReLU, the final conv, the loss and the confusion counts read the last
+                # convolution's output once (csrc/head_fused.cu)
+                conv_out, stats = self.decoder[idx].forward_cl(skip, h, impl, defer_last_norm=True)
+                mode, alpha, beta, want_conf, target = head
+                loss, logits, conf = F.fused_head(conv_out, stats, self.decoder[idx].double_conv[5], self.final_conv, target, mode, alpha, beta,
+                                                  want_conf, round_bf16=True)
+                return logits, bott, loss, conf
             h = self.decoder[idx].forward_cl(skip, h, impl)  # virtual cat((skip, up), 1)
         logits = F.final_conv1x1(h, self.final_conv.weight, self.final_conv.bias, round_bf16=(dtype == torch.bfloat16))
         if self.output_activation is not None:
@@ -151,3 +163,27 @@ class UNet3D(nn.Module):
 
     def forward(self, x):
         return self._body(x)[0]
+
+    def fused_head_available(self, x) -> bool:
+        """The single-pass head serves the training configuration of the reference's scripts: train mode, bf16 compute, 16 features at
+        the top level, 2..4 classes, no output activation, no dropout after the last convolution."""
+        last = self.decoder[-1].double_conv if len(self.decoder) else None
+        return bool(self.training and last is not None and len(self.upconvs) > 0 and x.is_cuda and _compute_dtype(self, x) == torch.bfloat16
+                    and last[4].out_channels == 16 and 2 <= self.final_conv.out_channels <= 4 and self.output_activation is None
+                    and last[7].p <= 0.0 and last[5].training and last[5].momentum is not None and self.final_conv.in_channels == 16)
+
+    def forward_with_loss(self, x, target, loss_fn, want_confusion=False):
+        """``(logits, loss, confusion)`` with ``loss == loss_fn(model(x).float(), target)`` (``loss_fn`` one of this package's
+        ``utils.metrics`` losses) and ``confusion`` the int64 ``[C, C]`` counts ``conf[target, argmax]`` (or None).  When the
+        configuration allows (``fused_head_available``) everything after the last convolution runs as one kernel per direction;
+        otherwise this is exactly the unfused sequence.  ``target`` may be int64 (the reference's contract) or uint8."""
+        spec = getattr(loss_fn, "_b200_spec", None)
+        if spec is not None and self.fused_head_available(x):
+            mode, alpha, beta = spec
+            logits, _, loss, conf = self._body(x, head=(mode, alpha, beta, bool(want_confusion), target))
+            return logits, loss, conf
+        logits = self(x)
+        t = target if target.dtype == torch.int64 else target.long()
+        loss = loss_fn(logits.float(), t)
+        conf = F.confusion_counts(logits.detach(), t) if want_confusion else None
+        return logits, loss, conf

@@ -50,6 +50,13 @@ def dice_only_loss(pred, target):
     return F.seg_loss(pred, target, _lib.LOSS_DICE)
 
 
+# what UNet3D.forward_with_loss needs to run a loss inside the fused head: (mode, alpha, beta) of the default-argument call
+combined_loss._b200_spec = (_lib.LOSS_DICE_CE, 0.5, 0.5)
+tversky_loss._b200_spec = (_lib.LOSS_TVERSKY, 0.5, 0.5)
+combined_ce_tversky_loss._b200_spec = (_lib.LOSS_CE_TVERSKY, 0.7, 0.3)
+dice_only_loss._b200_spec = (_lib.LOSS_DICE, 0.5, 0.5)
+
+
 # ------------------------------------------------------------------ multi-class metrics (reference :65-129)
 def _confusion(pred, target):
     # One argmax + confusion-count pass per call.  There is deliberately NO cache across calls: libb200unet kernels and

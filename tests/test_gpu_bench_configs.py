@@ -316,7 +316,9 @@ def _nccl_worker(rank, world, port, size, steps, out_dir):
     torch.cuda.synchronize()
     torch.save({"flat": tr.fp.flat.cpu(), "start": start.cpu(), "order": [n for n, _ in tr.fp.order]}, os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
+    # leave without tearing NCCL down: destroy_process_group() can dead-lock while a captured graph still references the communicator
+    os._exit(0)
 
 
 @pytest.mark.parametrize("size", [32, 64])
