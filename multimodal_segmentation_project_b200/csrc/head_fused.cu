@@ -60,20 +60,53 @@ __device__ __forceinline__ void bn_relu16(const uint4 (&raw)[2], const float* __
   }
 }
 
+// BatchNorm + ReLU of one voxel's 16 channels with the parameters read from shared memory as float4 (one read serves the U
+// voxels a thread handles per iteration); the bf16 rounding and the ReLU run on packed pairs (one F2FP + one HMNMX2 per pair).
+template <int U>
+__device__ __forceinline__ void bn_relu16_multi(const uint4 (&raw)[U][2], const float4* __restrict__ sc4, const float4* __restrict__ sh4,
+                                                const float4* __restrict__ mu4, float (&y)[U][CIN]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 sc = sc4[q], sh = sh4[q], mu = mu4[q];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t w0 = q < 2 ? (q == 0 ? raw[u][0].x : raw[u][0].z) : (q == 2 ? raw[u][1].x : raw[u][1].z);
+      const uint32_t w1 = q < 2 ? (q == 0 ? raw[u][0].y : raw[u][0].w) : (q == 2 ? raw[u][1].y : raw[u][1].w);
+      const float t0 = fmaf(__uint_as_float(w0 << 16) - mu.x, sc.x, sh.x), t1 = fmaf(__uint_as_float(w0 & 0xffff0000u) - mu.y, sc.y, sh.y);
+      const float t2 = fmaf(__uint_as_float(w1 << 16) - mu.z, sc.z, sh.z), t3 = fmaf(__uint_as_float(w1 & 0xffff0000u) - mu.w, sc.w, sh.w);
+      const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+      const __nv_bfloat162 p01 = __hmax2(__floats2bfloat162_rn(t0, t1), zero), p23 = __hmax2(__floats2bfloat162_rn(t2, t3), zero);
+      const uint32_t b01 = *reinterpret_cast<const uint32_t*>(&p01), b23 = *reinterpret_cast<const uint32_t*>(&p23);
+      y[u][4 * q] = __uint_as_float(b01 << 16);
+      y[u][4 * q + 1] = __uint_as_float(b01 & 0xffff0000u);
+      y[u][4 * q + 2] = __uint_as_float(b23 << 16);
+      y[u][4 * q + 3] = __uint_as_float(b23 & 0xffff0000u);
+    }
+  }
+}
+
 // sums layout = seg_loss_fwd's (loss_kernels.cu): [0] CE sum, per class k: [4+4k] I, [5+4k] P, [6+4k] T
+// ncu of the first version (one voxel per thread and iteration, scalar shared-memory parameter reads): 506 warp instructions per
+// 32 voxels, 112 of them LDS, issue-bound at 109 us.  Now: U = 2 voxels per thread share float4 parameter reads.
 template <typename LabelT>
 __global__ void __launch_bounds__(kThreads)
 head_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                 const float* __restrict__ w, const float* __restrict__ bias, int round_bf16, const LabelT* __restrict__ target, int64_t N,
                 int64_t S, int C, float* __restrict__ logits, double* __restrict__ sums, unsigned long long* __restrict__ conf) {
-  __shared__ float ws[CMAX * CIN + CMAX + 3 * CIN];
+  constexpr int U = 2;
+  __shared__ __align__(16) float ws[CMAX * CIN + 3 * CIN];
   __shared__ unsigned int hist[kThreads / 32][CMAX * CMAX];
   __shared__ float red[kThreads / 32][1 + 3 * CMAX];
-  float* bs = ws + CMAX * CIN;
-  float* sc = bs + CMAX; float* sh = sc + CIN; float* mu = sh + CIN;
+  const float4* w4 = reinterpret_cast<const float4*>(ws);
+  const float4* sc4 = w4 + CMAX * CIN / 4; const float4* sh4 = sc4 + CIN / 4; const float4* mu4 = sh4 + CIN / 4;
   for (int i = threadIdx.x; i < CMAX * CIN; i += blockDim.x) ws[i] = i < C * CIN ? w[i] : 0.f;
-  if (threadIdx.x < CMAX) bs[threadIdx.x] = (bias && threadIdx.x < C) ? bias[threadIdx.x] : 0.f;
-  if (threadIdx.x < CIN) { sc[threadIdx.x] = scale[threadIdx.x]; sh[threadIdx.x] = shift[threadIdx.x]; mu[threadIdx.x] = mean[threadIdx.x]; }
+  if (threadIdx.x < CIN) {
+    ws[CMAX * CIN + threadIdx.x] = scale[threadIdx.x]; ws[CMAX * CIN + CIN + threadIdx.x] = shift[threadIdx.x];
+    ws[CMAX * CIN + 2 * CIN + threadIdx.x] = mean[threadIdx.x];
+  }
+  float br[CMAX];
+#pragma unroll
+  for (int co = 0; co < CMAX; ++co) br[co] = (bias && co < C) ? bias[co] : 0.f;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane < CMAX * CMAX) hist[warp][lane] = 0;
   __syncthreads();
@@ -81,48 +114,78 @@ head_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ scale, con
   float ce = 0.f, accI[CMAX], accP[CMAX], accT[CMAX];
 #pragma unroll
   for (int c = 0; c < CMAX; ++c) accI[c] = accP[c] = accT[c] = 0.f;
-  const int64_t total = N * S, stride = (int64_t)gridDim.x * blockDim.x;
-  // every lane of a warp runs the same number of iterations (match_any below needs the full mask)
-  for (int64_t vb = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); vb < total; vb += stride) {
-    const int64_t v = vb + lane;
-    const bool active = v < total;
-    int key = -1;
-    if (active) {
-      uint4 raw[2];
-      raw[0] = __ldcs(reinterpret_cast<const uint4*>(x + v * CIN));
-      raw[1] = __ldcs(reinterpret_cast<const uint4*>(x + v * CIN) + 1);
-      const long long yy = (long long)target[v];
-      float xc[CIN], y[CIN], z[CMAX];
-      bn_relu16(raw, sc, sh, mu, xc, y);
+  // every sample is walked separately (no 64-bit division per voxel); a warp covers 32 consecutive voxels, U such rows per
+  // iteration, and all its lanes run the same number of iterations (match_any below needs the full mask)
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t n = 0; n < N; ++n) {
+    const bf16* xn = x + n * S * CIN;
+    const LabelT* tn = target + n * S;
+    float* ln = logits + n * C * S;
+    for (int64_t vb = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); vb < S; vb += U * stride) {
+      uint4 raw[U][2];
+      long long yy[U];
+      bool act[U];
 #pragma unroll
-      for (int co = 0; co < CMAX; ++co) {
-        float a = bs[co];
-#pragma unroll
-        for (int k = 0; k < CIN; ++k) a = fmaf(y[k], ws[co * CIN + k], a);
-        z[co] = round_bf16 ? __bfloat162float(__float2bfloat16_rn(a)) : a;
+      for (int u = 0; u < U; ++u) {
+        const int64_t v = vb + u * stride + lane;
+        act[u] = v < S;
+        raw[u][0] = raw[u][1] = make_uint4(0, 0, 0, 0);
+        yy[u] = -1;
+        if (act[u]) {
+          raw[u][0] = __ldcs(reinterpret_cast<const uint4*>(xn + v * CIN));
+          raw[u][1] = __ldcs(reinterpret_cast<const uint4*>(xn + v * CIN) + 1);
+          yy[u] = (long long)tn[v];
+        }
       }
-      const int64_t n = v / S, sp = v - n * S;
+      float y[U][CIN], z[U][CMAX];
+      bn_relu16_multi<U>(raw, sc4, sh4, mu4, y);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int co = 0; co < CMAX; ++co) z[u][co] = br[co];
+      // the unfused 1x1 kernel's fma chain (channels in ascending order from the bias): logits stay bit-identical
 #pragma unroll
       for (int co = 0; co < CMAX; ++co)
-        if (co < C) logits[(n * C + co) * S + sp] = z[co];
-      Softmax4 sm;
-      sm.compute(z, C);
-      float zy = 0.f;
-      float best = z[0];
-      int arg = 0;
 #pragma unroll
-      for (int c = 0; c < CMAX; ++c)
-        if (c < C) {
-          accP[c] += sm.p[c];
-          if (c == yy) { accI[c] += sm.p[c]; accT[c] += 1.f; zy = z[c]; }
-          if (c > 0 && better(z[c], best)) { best = z[c]; arg = c; }
+        for (int q = 0; q < 4; ++q) {
+          const float4 wv = w4[co * 4 + q];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            z[u][co] = fmaf(y[u][4 * q], wv.x, z[u][co]);
+            z[u][co] = fmaf(y[u][4 * q + 1], wv.y, z[u][co]);
+            z[u][co] = fmaf(y[u][4 * q + 2], wv.z, z[u][co]);
+            z[u][co] = fmaf(y[u][4 * q + 3], wv.w, z[u][co]);
+          }
         }
-      ce += sm.lse - zy;
-      key = (yy >= 0 && yy < C) ? (int)yy * C + arg : -1;
-    }
-    if (conf) {
-      const unsigned peers = __match_any_sync(0xffffffffu, key);
-      if (key >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(&hist[warp][key], (unsigned)__popc(peers));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        int key = -1;
+        if (act[u]) {
+          const int64_t v = vb + u * stride + lane;
+#pragma unroll
+          for (int co = 0; co < CMAX; ++co) {
+            if (round_bf16) z[u][co] = __bfloat162float(__float2bfloat16_rn(z[u][co]));
+            if (co < C) ln[co * S + v] = z[u][co];
+          }
+          Softmax4 sm;
+          sm.compute(z[u], C);
+          float zy = 0.f, best = z[u][0];
+          int arg = 0;
+#pragma unroll
+          for (int c = 0; c < CMAX; ++c)
+            if (c < C) {
+              accP[c] += sm.p[c];
+              if (c == yy[u]) { accI[c] += sm.p[c]; accT[c] += 1.f; zy = z[u][c]; }
+              if (c > 0 && better(z[u][c], best)) { best = z[u][c]; arg = c; }
+            }
+          ce += sm.lse - zy;
+          key = (yy[u] >= 0 && yy[u] < C) ? (int)yy[u] * C + arg : -1;
+        }
+        if (conf) {
+          const unsigned peers = __match_any_sync(0xffffffffu, key);
+          if (key >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(&hist[warp][key], (unsigned)__popc(peers));
+        }
+      }
     }
   }
   ce = warp_sum(ce);
@@ -278,7 +341,7 @@ extern "C" int b200_head_fwd(const void* x, const float* scale, const float* shi
   cudaStream_t st = (cudaStream_t)stream;
   B200_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * (4 + 4 * C), st));
   if (conf) B200_CUDA(cudaMemsetAsync(conf, 0, sizeof(unsigned long long) * C * C, st));
-  const int grid = b200_grid_for(N * S, kThreads, B200_NUM_SMS * 8);
+  const int grid = b200_grid_for(S, 2 * kThreads, B200_NUM_SMS * 6);
   if (label_bytes == 1)
     head_fwd_kernel<uint8_t><<<grid, kThreads, 0, st>>>((const bf16*)x, scale, shift, mean, w, bias, round_bf16, (const uint8_t*)target, N, S, C, logits, sums, conf);
   else
