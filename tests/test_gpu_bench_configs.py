@@ -321,6 +321,36 @@ def _nccl_worker(rank, world, port, size, steps, out_dir):
     os._exit(0)
 
 
+def _nccl_eval_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    net = UNet3D(1, 4, dropout_rate=0.0).cuda()
+    net.load_state_dict(init_state_dict(1, 4, seed=0))
+    vol, lab = structured_volume(1, (72, 64, 64), seed=31)
+    logits, conf, organs = evaluate_volume(net, vol.cuda(), lab.cuda(), window=32, stride=16)
+    torch.save({"conf": conf, "organs": organs, "slab": tuple(logits.shape)}, os.path.join(out_dir, f"eval{rank}.pt"))
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)
+
+
+def test_two_gpu_sliding_window_counts(cuda_dev, tmp_path):
+    """cfg 5 on two ranks: each owns half of the planes, one 16 x int64 all-reduce; counts equal the single-process evaluation."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under `gpurun --gpus 2`)")
+    import torch.multiprocessing as mp
+    mp.spawn(_nccl_eval_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    e0, e1 = torch.load(tmp_path / "eval0.pt", weights_only=False), torch.load(tmp_path / "eval1.pt", weights_only=False)
+    net = UNet3D(1, 4, dropout_rate=0.0).cuda()
+    net.load_state_dict(init_state_dict(1, 4, seed=0))
+    vol, lab = structured_volume(1, (72, 64, 64), seed=31)
+    _, conf, organs = evaluate_volume(net, vol.cuda(), lab.cuda(), window=32, stride=16)
+    assert np.array_equal(e0["conf"], conf) and np.array_equal(e1["conf"], conf)
+    assert e0["organs"] == organs and e0["slab"] == (1, 4, 36, 64, 64)
+
+
 @pytest.mark.parametrize("size", [32, 64])
 def test_two_gpu_nccl_graph_step_matches_single_process_average(cuda_dev, tmp_path, size):
     """After K graph replays (early bucket all-reduced on the side stream inside the captured graph) every rank holds
@@ -346,9 +376,9 @@ def test_two_gpu_nccl_graph_step_matches_single_process_average(cuda_dev, tmp_pa
         total = torch.zeros_like(tr.fp.grad)
         for xc, yc in data:
             tr.fp.detach_grads()
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                out = net(xc)
-            M.combined_loss(out.float(), yc).backward()
+            with torch.autocast("cuda", dtype=torch.bfloat16):     # the trainer's own forward path (fused head)
+                _, loss, _ = net.forward_with_loss(xc, yc, M.combined_loss)
+            loss.backward()
             F.join_pending()
             tr.fp.gather_grads("all")
             total += tr.fp.grad

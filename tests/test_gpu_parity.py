@@ -804,3 +804,32 @@ def test_conv3d_rowstream_vs_oracle(cuda_dev, case):
     # run-to-run determinism
     y0b, y1b = F.conv3d_k3_raw(x0, x1, wp, b.to(cuda_dev), co0, co1, impl=2)
     assert torch.equal(cf(y0b) if y1b is None else torch.cat([cf(y0b), cf(y1b)], dim=1), outs[0])
+
+
+def test_unet_out_channels_1_constructor_default(cuda_dev):
+    """The reference constructor's default is out_channels=1 (models/unet.py:35); every call site passes 4.  Forward and backward of
+    the one-channel head against the oracle, fp32 and bf16 (the fused 2..4-class head does not apply: generic kernels)."""
+    sd = init_state_dict(1, 1, seed=2)
+    assert tuple(sd["final_conv.weight"].shape) == (1, 16, 1, 1, 1)
+    x, _ = structured_volume(2, 16, seed=3)
+    tgt = torch.randn(2, 1, 16, 16, 16, generator=torch.Generator().manual_seed(5))
+    p = {k: v.clone() for k, v in sd.items()}
+    for k in p:
+        if p[k].is_floating_point() and "running" not in k:
+            p[k].requires_grad_(True)
+    ref_logits = unet3d_forward(p, x, True)
+    ((ref_logits - tgt) ** 2).mean().backward()
+    net = _net_from(sd, in_channels=1, out_channels=1, dropout_rate=0.0).train()
+    logits = net(x.cuda())
+    assert tuple(logits.shape) == (2, 1, 16, 16, 16)
+    ((logits - tgt.cuda()) ** 2).mean().backward()
+    assert rel_l2(logits, ref_logits) <= 1e-4
+    keys = [k for k, _ in net.named_parameters() if not (k.endswith("double_conv.0.bias") or k.endswith("double_conv.4.bias"))]
+    named = dict(net.named_parameters())
+    ours = torch.cat([named[k].grad.flatten().cpu() for k in keys])
+    ref = torch.cat([p[k].grad.flatten() for k in keys])
+    assert rel_l2(ours, ref) <= 5e-4
+    net.zero_grad()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        lb = net(x.cuda())
+    assert rel_l2(lb, ref_logits) <= 3e-2 and lb.dtype == torch.float32

@@ -423,3 +423,27 @@ def test_trainer_uses_fused_head_and_bf16_uint8_batches(cuda_dev):
         res.append((losses, tr.metrics.clone(), tr.fp.flat.clone()))
     assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
     assert int(res[0][1].sum()) == y.numel()
+
+
+@pytest.mark.gpu
+def test_sliding_window_output_sharding_matches_single_rank(cuda_dev):
+    """Multi-GPU evaluation shards the OUTPUT volume into D-slabs (inference.owned_slab): the slabs of 1, 2 and 3 'ranks', computed
+    one after the other here, tile the single-rank result bit for bit, and their confusion counts add up to the global counts —
+    which is all that crosses NVLink (one C x C int64 all-reduce)."""
+    from multimodal_segmentation_project_b200.inference import _slab_logits, owned_slab
+    sd = init_state_dict(1, 4, seed=0)
+    vol, lab = structured_volume(1, (40, 48, 32), seed=31)
+    net = UNet3D(1, 4, dropout_rate=0.0).cuda(); net.load_state_dict(sd); net.eval()
+    volc, labc = vol.cuda(), lab.cuda()
+    full, conf, _ = evaluate_volume(net, volc, labc, window=32, stride=16)
+    for world in (2, 3, 7):
+        parts, total = [], np.zeros((4, 4), dtype=np.int64)
+        for rank in range(world):
+            d_lo, d_hi = owned_slab(40, rank, world)
+            if d_hi <= d_lo:
+                continue
+            slab = _slab_logits(net, volc, (32, 32, 32), (16, 16, 16), d_lo, d_hi)
+            parts.append(slab)
+            total += F.confusion_counts(slab, labc[:, :, d_lo:d_hi].contiguous()).cpu().numpy()
+        assert torch.equal(torch.cat(parts, dim=2), full), world
+        assert np.array_equal(total, conf)
