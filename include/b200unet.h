@@ -92,6 +92,11 @@ int64_t b200_pack_conv3_bytes(int mode, int dtype, int Cout, int Cin);
  */
 /* resolves impl=0 (auto) for a given problem: returns 1 (CUDA-core, B200_PACK_FPROP/DGRAD weights) or
  * 2 (tcgen05, B200_PACK_*_TC weights); the caller packs the weights accordingly. */
+/* every tcgen05 weight layout of a model in ONE launch (once per optimiser step): `jobs` = device array of njobs + 1 records
+ * { const float* w; void* out; int32 Cout, Cin, dgrad, pad; int64 group_begin } (40 bytes; group_begin counts 16-byte output
+ * groups, 27*Cin*Cout/8 per job; record njobs carries the total).  out = what b200_pack_conv3_weights(mode FPROP_TC / DGRAD_TC)
+ * writes for that layer. */
+int b200_pack_conv3_batched(const void* jobs, int njobs, int64_t total_groups, void* stream);
 int b200_conv3d_k3_select(int dtype, int impl, int c0, int c1, int co0, int co1, int N, int D, int H, int W);
 /* selects the persistent tcgen05 convolution (one CTA per SM looping over tiles, double-buffered TMEM):
  * 0 never, 1 auto (default: every layer with >= 2 tiles per SM and <= 64 output channels per tile), 2 same as 1,

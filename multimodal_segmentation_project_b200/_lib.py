@@ -47,6 +47,7 @@ def _declare(lib) -> None:
         "b200_cast_to_f32": (I, [I, P, P, L, P]),
         "b200_pack_conv3_weights": (I, [I, I, P, P, I, I, P]),
         "b200_pack_conv3_bytes": (L, [I, I, I, I]),
+        "b200_pack_conv3_batched": (I, [P, I, L, P]),
         "b200_conv3d_k3_select": (I, [I, I, I, I, I, I, I, I, I, I]),
         "b200_set_conv_persistent": (I, [I]),
         "b200_set_conv_rowstream": (I, [I]),

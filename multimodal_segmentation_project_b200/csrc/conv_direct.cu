@@ -598,6 +598,16 @@ extern "C" int b200_pack_conv3_weights(int mode, int dtype, const float* w, void
   return B200_OK;
 }
 
+int b200_pack_conv3_batched_tc2(const void* jobs, int njobs, long long total_groups, cudaStream_t stream);
+
+// All tcgen05 weight layouts of a model in one launch: `jobs` = device array of njobs + 1 records
+// {const float* w; void* out; int32 Cout, Cin, dgrad, pad; int64 group_begin} (40 bytes each; group_begin counts 16-byte output
+// groups = 27 * Cin * Cout / 8 per job, record njobs carries the total).  Destinations are what b200_pack_conv3_weights would write.
+extern "C" int b200_pack_conv3_batched(const void* jobs, int njobs, int64_t total_groups, void* stream) {
+  B200_REQUIRE(tc_version() == 2, B200_ERR_UNSUPPORTED, "pack_conv3_batched: only the current tcgen05 weight layout is supported");
+  return b200_pack_conv3_batched_tc2(jobs, njobs, total_groups, (cudaStream_t)stream);
+}
+
 extern "C" int b200_conv3d_k3_select(int dtype, int impl, int c0, int c1, int co0, int co1, int N, int D, int H, int W) {
   if (impl == 1 || impl == 2) return impl;
   return (dtype == B200_BF16 && b200_conv3d_k3_tc_supported(c0, c1, co0, co1, N, D, H, W)) ? 2 : 1;

@@ -288,7 +288,47 @@ __global__ void __launch_bounds__(256) pack_k3_tc2_kernel(const float* __restric
   }
 }
 
-inline int n_tile_for(int cout) { return cout <= 128 ? cout : 128; }
+__host__ __device__ inline int n_tile_for(int cout) { return cout <= 128 ? cout : 128; }
+
+// Every packed layout of every layer in ONE launch (the trainer calls this once per optimiser step instead of one pack kernel per
+// layer and direction: 34 dependent ~3 us kernels on the step's main chain).  Job table in device memory, built once by the host.
+struct PackJob {
+  const float* w;          // torch weight [Cout][Cin][3][3][3] fp32
+  bf16* out;               // packed destination
+  int Cout, Cin, dgrad, pad;
+  long long group_begin;   // first 16-byte group of this job in the global numbering; job njobs holds the total
+};
+static_assert(sizeof(PackJob) == 40, "PackJob layout is part of the C ABI (b200_pack_conv3_batched)");
+constexpr int kMaxPackJobs = 128;
+
+__global__ void __launch_bounds__(256) pack_k3_tc2_batched_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  __shared__ PackJob sj[kMaxPackJobs + 1];
+  for (int i = threadIdx.x; i <= njobs; i += blockDim.x) sj[i] = jobs[i];
+  __syncthreads();
+  const long long groups = sj[njobs].group_begin;
+  int j = 0;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < groups; gid += (long long)gridDim.x * blockDim.x) {
+    while (gid >= sj[j + 1].group_begin) ++j;              // gid only grows: the scan resumes where it stopped
+    const PackJob& q = sj[j];
+    const int conv_in = q.dgrad ? q.Cout : q.Cin, conv_out = q.dgrad ? q.Cin : q.Cout;
+    const uint32_t n_tile = (uint32_t)n_tile_for(conv_out), slabs = (uint32_t)(conv_in / 16);
+    uint32_t t = (uint32_t)(gid - q.group_begin);
+    const uint32_t tap = t % 27; t /= 27;
+    const uint32_t kc = t % 2; t /= 2;
+    const uint32_t nn = t % n_tile; t /= n_tile;
+    const uint32_t slab = t % slabs;
+    const uint32_t nchunk = t / slabs;
+    const uint32_t kd = tap / 9, khw = tap % 9, k0 = slab * 16 + kc * 8, o = nchunk * n_tile + nn;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      f[e] = !q.dgrad ? q.w[((int64_t)o * q.Cin + (k0 + e)) * 27 + tap] : q.w[((int64_t)(k0 + e) * q.Cin + o) * 27 + (26 - tap)];
+    Vec8<bf16> v;
+    v.set(f);
+    const uint32_t g = ((((nchunk * slabs + slab) * 9 + khw) * 2 + kc) * 3 + kd) * n_tile + nn;
+    v.store(q.out + (int64_t)g * 8);
+  }
+}
 
 // split-K epilogue: y = bf16(sum_z partial[z] + bias), channels [0,co0) -> y0, [co0, co0+co1) -> y1
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int ksplit, int64_t rows, int cout, const float* __restrict__ bias,
@@ -365,6 +405,13 @@ int b200_pack_conv3_weights_tc2(int mode, const float* w, void* out, int Cout, i
   const int64_t total = (int64_t)27 * Cin * Cout;
   pack_k3_tc2_kernel<<<b200_grid_for(total / 8, 256, B200_NUM_SMS * 4), 256, 0, stream>>>(w, (bf16*)out, Cout, Cin, dgrad, n_tile, slabs, total);
   B200_CHECK_LAUNCH("pack_conv3_weights_tc2");
+  return B200_OK;
+}
+
+int b200_pack_conv3_batched_tc2(const void* jobs, int njobs, long long total_groups, cudaStream_t stream) {
+  B200_REQUIRE(jobs && njobs > 0 && njobs <= kMaxPackJobs, B200_ERR_SHAPE, "pack_conv3_batched: 1..%d jobs", kMaxPackJobs);
+  pack_k3_tc2_batched_kernel<<<b200_grid_for(total_groups, 256, B200_NUM_SMS * 4), 256, 0, stream>>>((const PackJob*)jobs, njobs);
+  B200_CHECK_LAUNCH("pack_conv3_batched");
   return B200_OK;
 }
 

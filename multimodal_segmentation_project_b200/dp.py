@@ -244,6 +244,7 @@ class DataParallelTrainer:
             loss.backward()
             self.allreduce_grads()
             self.opt.step(grad_scale=1.0 / self.world)
+            self._repack()
         else:
             (loss / self.accum).backward()
             self._join_wgrads()
@@ -254,6 +255,7 @@ class DataParallelTrainer:
                     for t in self.fp.buckets():
                         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
                 self.opt.step(grad_scale=1.0 / self.world)
+                self._repack()
         if want_conf:
             if conf is None:
                 from .functional import confusion_counts
@@ -262,6 +264,13 @@ class DataParallelTrainer:
         else:
             metrics = self.metrics_fn(logits.detach(), y) if self.metrics_fn is not None else None
         return loss.detach(), metrics
+
+    def _repack(self):
+        # the conv kernels' bf16 weight layouts follow the new fp32 parameters: one batched kernel per step
+        # (functional.repack_cached_weights) instead of one pack kernel per layer and direction
+        if self.fp.flat.is_cuda:
+            from . import functional as F
+            F.repack_cached_weights()
 
     def step(self, x, y):
         """Eager step on device tensors."""
@@ -297,6 +306,7 @@ class DataParallelTrainer:
         if y is not None:
             self.static_y.copy_(y, non_blocking=True)
         self._sync_hyper()
+        self._refresh_derived()
         self.graph.replay()
         return self.loss
 
@@ -313,6 +323,23 @@ class DataParallelTrainer:
         self._loss_ring[i].copy_(loss, non_blocking=True)
         self._loss_events[i].record(torch.cuda.current_stream())
         return _LossHandle(self._loss_ring[i], self._loss_events[i])
+
+    def load_flat(self, flat: torch.Tensor):
+        """Overwrites all parameters from a flat fp32 vector laid out like ``self.fp.flat`` (e.g. to rewind to a saved point) and
+        refreshes everything derived from them.  Writing ``self.fp.flat`` directly bypasses torch's version counters: call
+        ``functional.weights_changed()`` afterwards if you do."""
+        self.fp.flat.copy_(flat)
+        if self.fp.flat.is_cuda:
+            from . import functional as F
+            F.weights_changed()
+            F.repack_cached_weights()
+
+    def _refresh_derived(self):
+        # parameters changed outside the captured step (load_state_dict, load_flat, ...): the graph no longer repacks per layer
+        if self.fp.flat.is_cuda:
+            from . import functional as F
+            if F.cached_weights_stale():
+                F.repack_cached_weights()
 
     def _sync_hyper(self):
         # a scheduler (ReduceLROnPlateau, train_unet.py:381,442) edits param_groups between steps: push lr to the device word
@@ -348,5 +375,6 @@ class DataParallelTrainer:
         self.static_y.copy_(self._stage[1])
         self._stage_free.record(cur)
         self._sync_hyper()
+        self._refresh_derived()
         self.graph.replay()
         return self.loss

@@ -10,8 +10,8 @@ test infrastructure and is never imported from here).
 from __future__ import annotations
 
 import ctypes
-
 import os
+import weakref
 
 import torch
 
@@ -99,15 +99,99 @@ class _ToChannelsLast(torch.autograd.Function):
         return to_channels_first_f32(g), None
 
 
+# ---- packed tcgen05 weight layouts: cached per parameter, refreshed in ONE launch per optimiser step -------------------------
+# The conv kernels read weights in a bf16 UMMA layout derived from the fp32 nn.Parameter.  Deriving it per call costs one small
+# dependent kernel per layer and direction (34 per train step).  Cache entries are keyed on the parameter OBJECT and validated
+# against (data_ptr, torch's in-place version counter, this module's weights epoch): torch-side mutation (optimizer.step of a
+# torch optimizer, load_state_dict, ...) bumps _version; kernels of this library that write parameters through raw pointers
+# (FlatAdamW) bump the epoch with weights_changed().  A trainer then calls repack_cached_weights() once: one batched kernel
+# rewrites every cached layout in place (stable addresses: safe inside a captured CUDA graph).
+_weights_epoch = 0
+_pack_cache = {}          # (id(param), mode) -> dict(ref, packed, ptr, version, epoch, Cout, Cin)
+_pack_jobs = None         # (key tuple, device job table, njobs, total_groups)
+
+
+def weights_changed() -> None:
+    """Call after a kernel of this library wrote parameters through raw pointers (no torch version bump)."""
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+def _pack_now(L, w, mode, dt, out, Cout, Cin):
+    check(L.b200_pack_conv3_weights(mode, dt, _ptr(w), _ptr(out), Cout, Cin, _stream()), "pack_conv3_weights")
+
+
 def pack_conv3_weights(weight: torch.Tensor, mode: int, dtype: torch.dtype) -> torch.Tensor:
     L = _lib.load()
-    w = _f32(weight)
-    Cout, Cin = w.shape[0], w.shape[1]
+    Cout, Cin = weight.shape[0], weight.shape[1]
     dt = _lib.B200_F32 if dtype == torch.float32 else _lib.B200_BF16
-    nbytes = L.b200_pack_conv3_bytes(mode, dt, Cout, Cin)
-    out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-    check(L.b200_pack_conv3_weights(mode, dt, _ptr(w), _ptr(out), Cout, Cin, _stream()), "pack_conv3_weights")
-    return out
+    cacheable = (mode in (_lib.PACK_FPROP_TC, _lib.PACK_DGRAD_TC) and isinstance(weight, torch.nn.Parameter) and weight.dtype == torch.float32
+                 and weight.is_contiguous() and _cache_packed_weights)
+    if not cacheable:
+        w = _f32(weight)
+        out = torch.empty(L.b200_pack_conv3_bytes(mode, dt, Cout, Cin), dtype=torch.uint8, device=w.device)
+        _pack_now(L, w, mode, dt, out, Cout, Cin)
+        return out
+    global _pack_jobs
+    key = (id(weight), mode)
+    e = _pack_cache.get(key)
+    if e is not None and (e["ref"]() is not weight or e["ptr"] != weight.data_ptr()):
+        e = None                                   # a different tensor behind the same id, or the parameter was re-homed
+    if e is None:
+        out = torch.empty(L.b200_pack_conv3_bytes(mode, dt, Cout, Cin), dtype=torch.uint8, device=weight.device)
+        e = {"ref": weakref.ref(weight, lambda _r, k=key: _pack_cache.pop(k, None)), "packed": out, "ptr": weight.data_ptr(), "version": None,
+             "epoch": None, "Cout": Cout, "Cin": Cin, "mode": mode}
+        _pack_cache[key] = e
+        _pack_jobs = None
+    if e["version"] != weight._version or e["epoch"] != _weights_epoch:
+        _pack_now(L, weight.detach(), mode, dt, e["packed"], Cout, Cin)
+        e["version"], e["epoch"] = weight._version, _weights_epoch
+    return e["packed"]
+
+
+def repack_cached_weights() -> int:
+    """Rewrites every cached packed layout from its parameter's CURRENT values in one kernel launch and marks the entries fresh.
+    Returns the number of layouts written (0 = nothing cached yet, no launch)."""
+    global _pack_jobs
+    L = _lib.load()
+    live = [(k, e) for k, e in _pack_cache.items() if e["ref"]() is not None]
+    if not live:
+        return 0
+    sig = tuple((k, e["ptr"], e["packed"].data_ptr()) for k, e in live)
+    if _pack_jobs is None or _pack_jobs[0] != sig:
+        import struct
+        buf, g = bytearray(), 0
+        for _, e in live:
+            buf += struct.pack("<QQiiiiq", e["ptr"], e["packed"].data_ptr(), e["Cout"], e["Cin"], int(e["mode"] == _lib.PACK_DGRAD_TC), 0, g)
+            g += 27 * e["Cin"] * e["Cout"] // 8
+        buf += struct.pack("<QQiiiiq", 0, 0, 0, 0, 0, 0, g)
+        dev = live[0][1]["packed"].device
+        table = torch.frombuffer(buf, dtype=torch.uint8).clone().to(dev)
+        _pack_jobs = (sig, table, len(live), g)
+    _, table, n, total = _pack_jobs
+    check(L.b200_pack_conv3_batched(_ptr(table), n, total, _stream()), "pack_conv3_batched")
+    for _, e in live:
+        w = e["ref"]()
+        e["version"], e["epoch"] = w._version, _weights_epoch
+    return n
+
+
+def cached_weights_stale() -> bool:
+    """True if a cached layout no longer matches its parameter as far as the host can tell (torch version counter, epoch).  A
+    captured graph does not contain per-layer pack kernels any more, so a trainer checks this before every replay and repacks."""
+    for e in _pack_cache.values():
+        w = e["ref"]()
+        if w is not None and (e["version"] != w._version or e["epoch"] != _weights_epoch or e["ptr"] != w.data_ptr()):
+            return True
+    return False
+
+
+_cache_packed_weights = os.environ.get("B200_CACHE_PACKED_WEIGHTS", "1") != "0"
+
+
+def set_cache_packed_weights(on: bool) -> None:
+    global _cache_packed_weights
+    _cache_packed_weights = bool(on)
 
 
 def conv3d_select_impl(x0, x1, co0, co1, impl=0) -> int:
@@ -982,6 +1066,7 @@ class FlatAdamW(torch.optim.Optimizer):
                               g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], float(grad_scale), _stream()),
             "adamw_flat",
         )
+        weights_changed()       # parameters were written through raw pointers: cached packed layouts are stale
 
     # ---- torch.optim.AdamW wire format ------------------------------------------------------------------------------
     def _slices(self):

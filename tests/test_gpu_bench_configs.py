@@ -162,7 +162,7 @@ def test_cfg2_graph_step_loss_matches_oracle(cuda_dev):
     tr = DataParallelTrainer(net, M.combined_loss, lr=1e-3, weight_decay=1e-2, autocast_dtype=torch.bfloat16)
     flat0 = tr.fp.flat.clone()
     tr.capture(xc, yc, warmup=3)             # warm-up steps move the weights: restore the starting point afterwards
-    tr.fp.flat.copy_(flat0)
+    tr.load_flat(flat0)
     tr.opt.m.zero_(); tr.opt.v.zero_(); tr.opt.step_count.zero_()
     ours = [tr.replay().item() for _ in range(3)]
     _log(test="cfg2_graph_step_losses", ours=ours, oracle=ref_losses)
@@ -309,7 +309,7 @@ def _nccl_worker(rank, world, port, size, steps, out_dir):
     tr = DataParallelTrainer(net, M.combined_loss, lr=1e-3, weight_decay=1e-2, autocast_dtype=torch.bfloat16)
     start = tr.fp.flat.clone()
     tr.capture(xc, yc, warmup=3)
-    tr.fp.flat.copy_(start)
+    tr.load_flat(start)
     tr.opt.m.zero_(); tr.opt.v.zero_(); tr.opt.step_count.zero_()
     for _ in range(steps):
         tr.replay()

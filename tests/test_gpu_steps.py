@@ -447,3 +447,61 @@ def test_sliding_window_output_sharding_matches_single_rank(cuda_dev):
             total += F.confusion_counts(slab, labc[:, :, d_lo:d_hi].contiguous()).cpu().numpy()
         assert torch.equal(torch.cat(parts, dim=2), full), world
         assert np.array_equal(total, conf)
+
+
+@pytest.mark.gpu
+def test_packed_weight_cache_follows_every_kind_of_weight_update(cuda_dev):
+    """The conv kernels' packed bf16 weights are cached and refreshed by ONE batched kernel per optimiser step.  Whatever changes
+    the parameters — torch optimiser (version counter), FlatAdamW inside a captured graph (epoch + in-graph repack), load_state_dict
+    between replays (checked before each replay), load_flat — the next forward sees the new weights."""
+    sd = init_state_dict(1, 4, seed=0)
+    sd2 = init_state_dict(1, 4, seed=9)
+    x, y = structured_volume(2, 32, seed=3)
+    xc, yc = x.cuda(), y.cuda()
+
+    def fresh_logits(state):
+        F.set_cache_packed_weights(False)
+        try:
+            net = UNet3D(1, 4, dropout_rate=0.0).cuda(); net.load_state_dict(state); net.eval()
+            with torch.autocast("cuda", dtype=torch.bfloat16), torch.no_grad():
+                return net(xc)
+        finally:
+            F.set_cache_packed_weights(True)
+
+    net = UNet3D(1, 4, dropout_rate=0.0).cuda(); net.load_state_dict(sd); net.eval()
+    with torch.autocast("cuda", dtype=torch.bfloat16), torch.no_grad():
+        n0 = F._lib.launch_count(); a = net(xc); first = F._lib.launch_count() - n0
+        n0 = F._lib.launch_count(); b = net(xc); second = F._lib.launch_count() - n0
+        assert torch.equal(a, b) and torch.equal(a, fresh_logits(sd))
+        assert second <= first - 16, (first, second)                     # 17 tcgen05 layers: no pack kernels the second time
+        net.load_state_dict(sd2)                                           # torch in-place copies: version counters move
+        assert torch.equal(net(xc), fresh_logits(sd2))
+        opt = torch.optim.SGD(net.parameters(), lr=0.1)
+        for q in net.parameters():
+            q.grad = torch.ones_like(q)
+        opt.step()
+        assert torch.equal(net(xc), fresh_logits(net.state_dict()))
+    # captured trainer: in-graph AdamW + repack; load_state_dict and load_flat between replays
+    tnet = UNet3D(1, 4, dropout_rate=0.0).cuda(); tnet.load_state_dict(sd); tnet.train()
+    tr = DataParallelTrainer(tnet, M.combined_loss, lr=1e-3, autocast_dtype=torch.bfloat16)
+    start = tr.fp.flat.clone()
+    tr.capture(xc, yc, warmup=2)
+    tr.load_flat(start); tr.opt.m.zero_(); tr.opt.v.zero_(); tr.opt.step_count.zero_()
+    l1 = [tr.replay().item() for _ in range(3)]
+    tr.load_flat(start); tr.opt.m.zero_(); tr.opt.v.zero_(); tr.opt.step_count.zero_()
+    l2 = [tr.replay().item() for _ in range(3)]
+    assert l1 == l2 and l1[0] != l1[1]
+    unet = UNet3D(1, 4, dropout_rate=0.0).cuda(); unet.load_state_dict(sd); unet.train()
+    F.set_cache_packed_weights(False)
+    try:
+        tu = DataParallelTrainer(unet, M.combined_loss, lr=1e-3, autocast_dtype=torch.bfloat16)
+        l3 = [tu.step(xc, yc).item() for _ in range(3)]
+    finally:
+        F.set_cache_packed_weights(True)
+    assert l1 == l3, (l1, l3)                                              # cached + graph == uncached + eager, bit for bit
+    tnet.load_state_dict(sd2)
+    tr.opt.m.zero_(); tr.opt.v.zero_(); tr.opt.step_count.zero_()
+    l4 = tr.replay().item()
+    vnet = UNet3D(1, 4, dropout_rate=0.0).cuda(); vnet.load_state_dict(sd2); vnet.train()
+    tv = DataParallelTrainer(vnet, M.combined_loss, lr=1e-3, autocast_dtype=torch.bfloat16)
+    assert l4 == tv.step(xc, yc).item()
