@@ -118,6 +118,16 @@ int b200_conv3d_k3_bnstats_blocks(int dtype, int impl, int c0, int c1, int co0, 
 int b200_conv3d_k3_bnstats(int dtype, int impl, const void* x0, int c0, const void* x1, int c1, const void* wpack,
                            const float* bias, void* y0, int co0, int N, int D, int H, int W, float* partials, void* stream);
 
+/* Data gradient of a convolution whose INPUT was relu(bn(xprev)) (the second conv of a DoubleConv, models/unet.py:15) + the
+ * BatchNorm-backward reduction of that previous layer in one kernel: y0 = gy and partials[rows][2][co0] = per-CTA
+ * (sum g, invstd * sum g * (xprev - mean)) with g = gy * [bn(xprev) > 0] (= b200_bn_act_bwd_reduce's partials, no dropout).
+ * rows = b200_conv3d_k3_bnbwd_blocks() (0: not served, run b200_conv3d_k3 + b200_bn_act_bwd_reduce); finish with
+ * b200_bn_bwd_finalize_ex(partials, rows, ...) and b200_bn_act_bwd_apply. */
+int b200_conv3d_k3_bnbwd_blocks(int dtype, int impl, int c0, int co0, int N, int D, int H, int W);
+int b200_conv3d_k3_bnbwd(int dtype, int impl, const void* x0, int c0, const void* wpack, void* y0, int co0, int N, int D, int H,
+                         int W, const void* xprev, const float* scale, const float* shift, const float* mean, const float* invstd,
+                         float* partials, void* stream);
+
 /* weight gradient of nn.Conv3d(k=3,p=1): dw[Cout, Cin, 3,3,3] fp32 (torch layout, overwritten),
  * dbias[Cout] fp32 (may be NULL).  workspace: b200_conv3d_wgrad_workspace() bytes. */
 int64_t b200_conv3d_wgrad_workspace(int c0, int c1, int Cout, int N, int D, int H, int W);

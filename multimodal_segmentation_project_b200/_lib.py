@@ -54,6 +54,8 @@ def _declare(lib) -> None:
         "b200_conv3d_k3": (I, [I, I, P, I, P, I, P, P, P, I, P, I, I, I, I, I, P]),
         "b200_conv3d_k3_bnstats_blocks": (I, [I, I, I, I, I, I, I, I, I, I]),
         "b200_conv3d_k3_bnstats": (I, [I, I, P, I, P, I, P, P, P, I, I, I, I, I, P, P]),
+        "b200_conv3d_k3_bnbwd_blocks": (I, [I, I, I, I, I, I, I, I]),
+        "b200_conv3d_k3_bnbwd": (I, [I, I, P, I, P, P, I, I, I, I, I, P, P, P, P, P, P, P]),
         "b200_conv3d_wgrad_workspace": (L, [I, I, I, I, I, I, I]),
         "b200_set_wgrad_impl": (I, [I]),
         "b200_debug_fail_next_wgrad": (I, [I]),

@@ -520,7 +520,9 @@ int b200_conv3d_k3_tc3_stats_blocks(int c0, int c1, int co0, int co1, int N, int
 bool b200_conv3d_k3_tc4_wanted(int c0, int c1, int co0, int co1, int N, int D, int H, int W);
 int b200_conv3d_k3_tc4_stats_blocks(int c0, int c1, int co0, int co1, int N, int D, int H, int W);
 int b200_conv3d_k3_tc4(const void* x0, int c0, const void* x1, int c1, const void* wpack, const float* bias, void* y0,
-                       int co0, void* y1, int co1, int N, int D, int H, int W, cudaStream_t stream, float* stats = nullptr);
+                       int co0, void* y1, int co1, int N, int D, int H, int W, cudaStream_t stream, float* stats = nullptr,
+                       const void* xprev = nullptr, const float* bn_scale = nullptr, const float* bn_shift = nullptr,
+                       const float* bn_mean = nullptr, const float* bn_invstd = nullptr);
 void b200_conv3d_k3_tc4_enable(int on);
 static bool conv_persistent_on(int c0, int c1, int co0, int co1);
 static int g_conv_persistent = -1;  // -1 unset (env B200_CONV_PERSISTENT or 1), 0 never, 1 auto, 2 whenever the layer has enough tiles
@@ -686,6 +688,25 @@ extern "C" int b200_conv3d_k3_bnstats(int dtype, int impl, const void* x0, int c
   if (b200_conv3d_k3_tc4_stats_blocks(c0, c1, co0, 0, N, D, H, W) > 0)
     return b200_conv3d_k3_tc4(x0, c0, x1, c1, wpack, bias, y0, co0, nullptr, 0, N, D, H, W, (cudaStream_t)stream, partials);
   return b200_conv3d_k3_tc3(x0, c0, x1, c1, wpack, bias, y0, co0, nullptr, 0, N, D, H, W, (cudaStream_t)stream, partials);
+}
+
+// Data gradient + BatchNorm-backward reduction in one kernel: y0 = gy (the gradient w.r.t. the previous layer's relu(bn(xprev))) and
+// partials[rows][2][co0] = per-CTA (sum g, invstd * sum g * (xprev - mean)), g = gy * [bn(xprev) > 0] — b200_bn_act_bwd_reduce's
+// output for that layer; rows = b200_conv3d_k3_bnbwd_blocks() (0: not available, run the separate pass).
+extern "C" int b200_conv3d_k3_bnbwd_blocks(int dtype, int impl, int c0, int co0, int N, int D, int H, int W) {
+  if (dtype != B200_BF16 || impl != 2 || tc_version() != 2 || !b200_conv3d_k3_tc_supported(c0, 0, co0, 0, N, D, H, W)) return 0;
+  if (!conv_persistent_on(c0, 0, co0, 0)) return 0;
+  return b200_conv3d_k3_tc4_stats_blocks(c0, 0, co0, 0, N, D, H, W);
+}
+
+extern "C" int b200_conv3d_k3_bnbwd(int dtype, int impl, const void* x0, int c0, const void* wpack, void* y0, int co0, int N, int D, int H,
+                                    int W, const void* xprev, const float* scale, const float* shift, const float* mean, const float* invstd,
+                                    float* partials, void* stream) {
+  B200_REQUIRE(x0 && wpack && y0 && xprev && partials, B200_ERR_SHAPE, "conv3d_k3_bnbwd: null pointer");
+  B200_REQUIRE(b200_conv3d_k3_bnbwd_blocks(dtype, impl, c0, co0, N, D, H, W) > 0, B200_ERR_UNSUPPORTED,
+               "conv3d_k3_bnbwd: no fused kernel serves this problem (ask b200_conv3d_k3_bnbwd_blocks first)");
+  return b200_conv3d_k3_tc4(x0, c0, nullptr, 0, wpack, nullptr, y0, co0, nullptr, 0, N, D, H, W, (cudaStream_t)stream, partials, xprev, scale,
+                            shift, mean, invstd);
 }
 
 /* 0 = never use the row-streaming kernel (conv_tc4.cu), 1 = wherever it applies (default) — tests and A/B timing */

@@ -54,6 +54,8 @@ struct Tc4Params {
   int stage_bytes;
   long long total_rows;      // N * dblocks * wtiles * H
   float* stats;
+  // BWD kernels: the output IS the gradient w.r.t. a BatchNorm+ReLU activation; xprev = that layer's pre-BN conv output
+  const bf16* xprev; const float* bn_scale; const float* bn_shift; const float* bn_mean; const float* bn_invstd;
   int skip;                  // B200_TC_DEBUG builds only
 };
 
@@ -101,7 +103,12 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int STATS_CH>
+// STATS_CH > 0, BWD = 0: BatchNorm batch statistics of the stored output (forward, as conv_tc3).
+// STATS_CH > 0, BWD = 1: the stored output gy is the gradient w.r.t. the activation relu(bn(xprev)) of the PREVIOUS layer (this launch
+// is a data gradient): the epilogue also reads xprev at the voxels it stores and accumulates the two channel sums of that
+// layer's BatchNorm backward, sum(g) and invstd * sum(g * (xprev - mean)) with g = gy * [bn(xprev) > 0] — the work of
+// bn_act_bwd_reduce (elementwise_kernels.cu) without its own pass over gy and xprev.
+template <int STATS_CH, int BWD>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_tc4_kernel(const Tc4Params p, const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -139,6 +146,11 @@ conv3d_tc4_kernel(const Tc4Params p, const __grid_constant__ CUtensorMap tm0, co
     if (p.c1) tma::prefetch(&tm1);
   }
   if (threadIdx.x >= 128 && threadIdx.x - 128 < p.n_t) bias_s[threadIdx.x - 128] = p.bias ? p.bias[threadIdx.x - 128] : 0.f;
+  float* bn_s = reinterpret_cast<float*>(smem + 640);     // BWD: [3][32] scale, shift, mean of the previous layer's BatchNorm
+  if (BWD && threadIdx.x >= 128 && threadIdx.x - 128 < p.n_t) {
+    const int c = threadIdx.x - 128;
+    bn_s[c] = p.bn_scale[c]; bn_s[32 + c] = p.bn_shift[c]; bn_s[64 + c] = p.bn_mean[c];
+  }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -310,11 +322,30 @@ conv3d_tc4_kernel(const Tc4Params p, const __grid_constant__ CUtensorMap tm0, co
       const bool wok = w < p.W;
       for (int h0 = sg.h_lo; h0 < sg.h_hi; ++h0, ++ord) {
         const int set = (int)(ord & (kSets - 1));
+        // BWD: the previous layer's pre-BN values of this row are fetched BEFORE waiting for the accumulator (their addresses do
+        // not depend on it): four 32-byte voxels per thread in flight behind the wait instead of one exposed round trip per plane
+        constexpr int kPre = (STATS_CH > 0 && BWD) ? 4 : 1;
+        uint4 xpre[kPre][2];
+        if (STATS_CH > 0 && BWD) {
+#pragma unroll
+          for (int j = 0; j < kPre; ++j) {
+            const int pi = STATS_CH == 16 ? j : (j >> 1), cc = STATS_CH == 16 ? 0 : (j & 1);
+            const int pl = grp * pl_per + pi;
+            const int64_t row = (((int64_t)sg.n * p.D + d0 + pl) * p.H + h0) * p.W + w;
+            xpre[j][0] = xpre[j][1] = make_uint4(0, 0, 0, 0);
+            if (wok && pl < planes) {
+              const uint4* xp = reinterpret_cast<const uint4*>(p.xprev + row * p.co0 + cc * 16);
+              xpre[j][0] = __ldcs(xp);
+              xpre[j][1] = __ldcs(xp + 1);
+            }
+          }
+        }
         tc::mbar_wait(acc_full(set), (uint32_t)((ord >> 2) & 1));
         tc::tc_fence_after();
         const uint32_t tset = tmem_base + lane_base + (uint32_t)set * kSetCols;
-#pragma unroll 1
-        for (int pi = 0; pi < (true TC4_DBG(&& !(p.skip & 4)) ? pl_per : 0); ++pi) {
+#pragma unroll
+        for (int pi = 0; pi < 4; ++pi) {
+          if (pi >= (true TC4_DBG(&& !(p.skip & 4)) ? pl_per : 0)) break;
           const int pl = grp * pl_per + pi;
           const uint32_t col0 = (uint32_t)(p.dseg - 1 - pl) * p.n_t;
           const bool valid = wok && pl < planes;
@@ -331,7 +362,7 @@ conv3d_tc4_kernel(const Tc4Params p, const __grid_constant__ CUtensorMap tm0, co
               const float2 bb = *reinterpret_cast<const float2*>(bias_s + cc * 16 + 2 * i);
               __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(v[2 * i]) + bb.x, __uint_as_float(v[2 * i + 1]) + bb.y);
               packed[i] = *reinterpret_cast<uint32_t*>(&hb);
-              if (STATS_CH > 0 && valid) {
+              if (STATS_CH > 0 && !BWD && valid) {
                 const float2 yv = __bfloat1622float2(hb);
                 const float e0 = yv.x - bb.x, e1 = yv.y - bb.y;
                 const int c = STATS_CH > 0 ? (cc * 16 + 2 * i) % STATS_CH : 0;
@@ -339,6 +370,25 @@ conv3d_tc4_kernel(const Tc4Params p, const __grid_constant__ CUtensorMap tm0, co
                 st_sq[c] = fmaf(e0, e0, st_sq[c]);
                 st_sum[STATS_CH > 0 ? c + 1 : 0] += e1;
                 st_sq[STATS_CH > 0 ? c + 1 : 0] = fmaf(e1, e1, st_sq[STATS_CH > 0 ? c + 1 : 0]);
+              }
+            }
+            if (STATS_CH > 0 && BWD && valid) {
+              const int j = (STATS_CH > 0 && BWD) ? (STATS_CH == 16 ? pi : pi * 2 + cc) : 0;
+              const uint4 xa = xpre[j][0], xb = xpre[j][1];
+              const uint32_t xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  const int c = STATS_CH > 0 ? (cc * 16 + 2 * i + hh) % STATS_CH : 0;
+                  const float xv = hh ? __uint_as_float(xw[i] & 0xffff0000u) : __uint_as_float(xw[i] << 16);
+                  const float gv = hh ? __uint_as_float(packed[i] & 0xffff0000u) : __uint_as_float(packed[i] << 16);
+                  const float xc = xv - bn_s[64 + c];
+                  const float pre = __bfloat162float(__float2bfloat16_rn(fmaf(xc, bn_s[c], bn_s[32 + c])));
+                  const float g = pre > 0.f ? gv : 0.f;
+                  st_sum[c] += g;
+                  st_sq[c] = fmaf(g, xc, st_sq[c]);
+                }
               }
             }
             if (valid) {
@@ -374,6 +424,7 @@ conv3d_tc4_kernel(const Tc4Params p, const __grid_constant__ CUtensorMap tm0, co
         float tot = 0.f;
 #pragma unroll
         for (int wq = 0; wq < 8; ++wq) tot += red[wq * 2 * STATS_CH + e];
+        if (BWD && e >= STATS_CH) tot *= p.bn_invstd[e - STATS_CH];
         p.stats[(size_t)blockIdx.x * 2 * STATS_CH + e] = tot;
       }
     }
@@ -444,7 +495,8 @@ int b200_conv3d_k3_tc4_stats_blocks(int c0, int c1, int co0, int co1, int N, int
 }
 
 int b200_conv3d_k3_tc4(const void* x0, int c0, const void* x1, int c1, const void* wpack, const float* bias, void* y0, int co0, void* y1,
-                       int co1, int N, int D, int H, int W, cudaStream_t stream, float* stats) {
+                       int co1, int N, int D, int H, int W, cudaStream_t stream, float* stats, const void* xprev, const float* bn_scale,
+                       const float* bn_shift, const float* bn_mean, const float* bn_invstd) {
   B200_REQUIRE(b200_aligned(x0, 16) && b200_aligned(x1, 16) && b200_aligned(y0, 16) && b200_aligned(y1, 16) && b200_aligned(wpack, 16),
                B200_ERR_ALIGN, "conv3d_k3(row-streaming): pointers must be 16-byte aligned");
   Plan pl;
@@ -459,6 +511,9 @@ int b200_conv3d_k3_tc4(const void* x0, int c0, const void* x1, int c1, const voi
   p.stage_bytes = pl.stage_bytes;
   p.total_rows = pl.rows;
   p.stats = stats;
+  p.xprev = (const bf16*)xprev; p.bn_scale = bn_scale; p.bn_shift = bn_shift; p.bn_mean = bn_mean; p.bn_invstd = bn_invstd;
+  B200_REQUIRE(!xprev || (stats && bn_scale && bn_shift && bn_mean && bn_invstd && b200_aligned(xprev, 16)), B200_ERR_SHAPE,
+               "conv3d_k3(row-streaming): the BatchNorm-backward epilogue needs partials, scale, shift, mean, invstd and an aligned xprev");
   p.skip = 0;
 #ifdef B200_TC_DEBUG
   { const char* e = getenv("B200_TC4_SKIP"); p.skip = e ? atoi(e) : 0; }
@@ -469,16 +524,20 @@ int b200_conv3d_k3_tc4(const void* x0, int c0, const void* x1, int c1, const voi
   if (c1) { rc = make_row_map(&tm1, x1, c1, N, D, H, W, pl.dseg + 2); if (rc) return rc; } else tm1 = tm0;
   static bool attr_set = false;
   if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(conv3d_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    B200_CUDA(cudaFuncSetAttribute(conv3d_tc4_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    B200_CUDA(cudaFuncSetAttribute(conv3d_tc4_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(conv3d_tc4_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(conv3d_tc4_kernel<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(conv3d_tc4_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(conv3d_tc4_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(conv3d_tc4_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int grid = (int)(pl.rows < B200_NUM_SMS ? pl.rows : B200_NUM_SMS);
   B200_REQUIRE(!stats || grid == B200_NUM_SMS, B200_ERR_UNSUPPORTED, "conv3d_k3(row-streaming): fused statistics expect a full grid");
-  if (stats && pl.n_t == 16) conv3d_tc4_kernel<16><<<grid, kThreads, pl.smem, stream>>>(p, tm0, tm1);
-  else if (stats) conv3d_tc4_kernel<32><<<grid, kThreads, pl.smem, stream>>>(p, tm0, tm1);
-  else conv3d_tc4_kernel<0><<<grid, kThreads, pl.smem, stream>>>(p, tm0, tm1);
+  if (stats && xprev && pl.n_t == 16) conv3d_tc4_kernel<16, 1><<<grid, kThreads, pl.smem, stream>>>(p, tm0, tm1);
+  else if (stats && xprev) conv3d_tc4_kernel<32, 1><<<grid, kThreads, pl.smem, stream>>>(p, tm0, tm1);
+  else if (stats && pl.n_t == 16) conv3d_tc4_kernel<16, 0><<<grid, kThreads, pl.smem, stream>>>(p, tm0, tm1);
+  else if (stats) conv3d_tc4_kernel<32, 0><<<grid, kThreads, pl.smem, stream>>>(p, tm0, tm1);
+  else conv3d_tc4_kernel<0, 0><<<grid, kThreads, pl.smem, stream>>>(p, tm0, tm1);
   B200_CHECK_LAUNCH("conv3d_k3_tc4");
   return B200_OK;
 }

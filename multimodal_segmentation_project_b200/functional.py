@@ -335,7 +335,9 @@ class _ConvBNAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x0, x1, weight, bias, gamma, beta, running_mean, running_var, nbt, dropmask, training, eps,
-                momentum, impl):
+                momentum, impl, prev_conv_out=None, prev_stats=None):
+        # prev_*: x0 == relu(bn(prev_conv_out)) of the previous _ConvBNAct (no dropout) — lets backward fold that layer's
+        # BatchNorm-backward reduction into this layer's data-gradient kernel
         _require_cuda(x0, x1, weight)
         L = _lib.load()
         ctx.impl_req = impl
@@ -387,43 +389,63 @@ class _ConvBNAct(torch.autograd.Function):
                               Cout, _stream()),
             "bn_act_fwd",
         )
-        ctx.save_for_backward(x0, x1, weight, conv_out, stats, dropmask)
+        ctx.save_for_backward(x0, x1, weight, conv_out, stats, dropmask, prev_conv_out, prev_stats)
         ctx.training = bool(training)
         ctx.has_bias = bias is not None
-        return y
+        ctx.mark_non_differentiable(conv_out, stats)
+        return y, conv_out, stats
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, _gconv=None, _gstats=None):
         L = _lib.load()
-        x0, x1, weight, conv_out, stats, dropmask = ctx.saved_tensors
+        x0, x1, weight, conv_out, stats, dropmask, prev_conv_out, prev_stats = ctx.saved_tensors
         gy = gy.contiguous()
         N, D, H, W, Cout = conv_out.shape
         M, S = N * D * H * W, D * H * W
         dev = gy.device
-        partials = _bn_partials(Cout, dev)
         dt = _dt(conv_out)
-        check(
-            L.b200_bn_act_bwd_reduce(dt, _ptr(gy), _ptr(conv_out), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]), _ptr(stats[3]),
-                                     _ptr(dropmask), 1, N, S, Cout, _ptr(partials), _stream()),
-            "bn_act_bwd_reduce",
-        )
         dgamma = torch.empty(Cout, dtype=torch.float32, device=dev)
         dbeta = torch.empty(Cout, dtype=torch.float32, device=dev)
         sums = torch.empty(2 * Cout, dtype=torch.float32, device=dev)
-        check(L.b200_bn_bwd_finalize(_ptr(partials), M, Cout, _ptr(dgamma), _ptr(dbeta), _ptr(sums), _stream()), "bn_bwd_finalize")
+        hit = _bnbwd_handoff.pop(conv_out.data_ptr(), None)
+        if hit is not None and hit[2] == gy.data_ptr() and dropmask is None:
+            # the kernel that produced gy (the next layer's data gradient) already reduced it against conv_out
+            check(L.b200_bn_bwd_finalize_ex(_ptr(hit[0]), hit[1], M, Cout, _ptr(dgamma), _ptr(dbeta), _ptr(sums), _stream()), "bn_bwd_finalize_ex")
+        else:
+            partials = _bn_partials(Cout, dev)
+            check(
+                L.b200_bn_act_bwd_reduce(dt, _ptr(gy), _ptr(conv_out), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]), _ptr(stats[3]),
+                                         _ptr(dropmask), 1, N, S, Cout, _ptr(partials), _stream()),
+                "bn_act_bwd_reduce",
+            )
+            check(L.b200_bn_bwd_finalize(_ptr(partials), M, Cout, _ptr(dgamma), _ptr(dbeta), _ptr(sums), _stream()), "bn_bwd_finalize")
         dconv = torch.empty_like(conv_out)
         check(
             L.b200_bn_act_bwd_apply(dt, _ptr(gy), _ptr(conv_out), _ptr(dconv), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]),
                                     _ptr(stats[3]), _ptr(dropmask), 1, _ptr(sums), int(ctx.training), N, S, Cout, _stream()),
             "bn_act_bwd_apply",
         )
-        dx0, dx1, dw, db = _conv_bwd_from_dconv(ctx, x0, x1, weight, dconv, zero_bias_grad=ctx.training)
-        return (dx0, dx1, dw, db, dgamma, dbeta, None, None, None, None, None, None, None, None)
+        dx0, dx1, dw, db = _conv_bwd_from_dconv(ctx, x0, x1, weight, dconv, zero_bias_grad=ctx.training, prev=(prev_conv_out, prev_stats))
+        return (dx0, dx1, dw, db, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None)
 
 
-def _conv_bwd_from_dconv(ctx, x0, x1, weight, dconv, zero_bias_grad):
+# (partials, rows, gy.data_ptr()) of a BatchNorm-backward reduction computed by the kernel that produced gy, keyed by the data
+# pointer of the conv_out it was taken against; written by the consumer layer's backward, popped by the producer layer's backward
+# within the same backward pass.
+_bnbwd_handoff = {}
+_fuse_bn_bwd = os.environ.get("B200_FUSE_BN_BWD", "1") != "0"
+
+
+def set_fuse_bn_bwd(on: bool) -> None:
+    """BatchNorm-backward reduction inside the data-gradient kernel of the following conv (default) or as its own pass."""
+    global _fuse_bn_bwd
+    _fuse_bn_bwd = bool(on)
+
+
+def _conv_bwd_from_dconv(ctx, x0, x1, weight, dconv, zero_bias_grad, prev=(None, None)):
     """Weight / bias / data gradients of the 3x3x3 convolution given d loss / d conv_out (shared by _ConvBNAct and _ConvStats).
-    zero_bias_grad: the bias feeds a batch-statistics BatchNorm, its gradient is exactly zero."""
+    zero_bias_grad: the bias feeds a batch-statistics BatchNorm, its gradient is exactly zero.
+    prev = (conv_out, stats) of the layer whose relu(bn(.)) is x0: its BatchNorm-backward sums ride on the data-gradient kernel."""
     dev = dconv.device
     Cout = dconv.shape[-1]
     dw = db = None
@@ -446,7 +468,20 @@ def _conv_bwd_from_dconv(ctx, x0, x1, weight, dconv, zero_bias_grad):
         c1 = 0 if x1 is None else x1.shape[-1]
         impl = conv3d_select_impl(dconv, None, c0, c1, ctx.impl_req)
         wpack = pack_conv3_weights(weight, pack_mode(impl, True), dconv.dtype)
-        dx0, dx1 = conv3d_k3_raw(dconv, None, wpack, None, c0, c1, impl)
+        L = _lib.load()
+        N, D, H, W, _ = dconv.shape
+        pco, pst = prev
+        rows = 0
+        if pco is not None and c1 == 0 and _fuse_bn_bwd and pco.shape == x0.shape and pco.dtype == dconv.dtype:
+            rows = L.b200_conv3d_k3_bnbwd_blocks(_dt(dconv), impl, Cout, c0, N, D, H, W)
+        if rows > 0:
+            dx0 = torch.empty_like(x0)
+            partials = _bn_partials(c0, dev)
+            check(L.b200_conv3d_k3_bnbwd(_dt(dconv), impl, _ptr(dconv), Cout, _ptr(wpack), _ptr(dx0), c0, N, D, H, W, _ptr(pco), _ptr(pst[0]),
+                                         _ptr(pst[1]), _ptr(pst[2]), _ptr(pst[3]), _ptr(partials), _stream()), "conv3d_k3_bnbwd")
+            _bnbwd_handoff[pco.data_ptr()] = (partials, rows, dx0.data_ptr())
+        else:
+            dx0, dx1 = conv3d_k3_raw(dconv, None, wpack, None, c0, c1, impl)
     join_side(side, dev, x0, x1, dconv, keep)
     del keep
     return dx0, dx1, dw, db
@@ -486,7 +521,7 @@ class _ConvStats(torch.autograd.Function):
     the fused head (_FusedHead) normalises on the fly.  Returns (conv_out, stats); the gradient arrives w.r.t. conv_out."""
 
     @staticmethod
-    def forward(ctx, x0, x1, weight, bias, gamma, beta, running_mean, running_var, nbt, eps, momentum, impl):
+    def forward(ctx, x0, x1, weight, bias, gamma, beta, running_mean, running_var, nbt, eps, momentum, impl, prev_conv_out=None, prev_stats=None):
         _require_cuda(x0, x1, weight)
         L = _lib.load()
         ctx.impl_req = impl
@@ -495,16 +530,16 @@ class _ConvStats(torch.autograd.Function):
         impl = conv3d_select_impl(x0, x1, weight.shape[0], 0, impl)
         conv_out, stats = _conv_and_batch_stats(L, x0, x1, weight, bias, gamma.detach(), beta.detach(), running_mean, running_var, nbt, eps,
                                                 momentum, impl)
-        ctx.save_for_backward(x0, x1, weight)
+        ctx.save_for_backward(x0, x1, weight, prev_conv_out, prev_stats)
         ctx.has_bias = bias is not None
         ctx.mark_non_differentiable(stats)
         return conv_out, stats
 
     @staticmethod
     def backward(ctx, dconv, _gstats):
-        x0, x1, weight = ctx.saved_tensors
-        dx0, dx1, dw, db = _conv_bwd_from_dconv(ctx, x0, x1, weight, dconv.contiguous(), zero_bias_grad=True)
-        return (dx0, dx1, dw, db, None, None, None, None, None, None, None, None)
+        x0, x1, weight, prev_conv_out, prev_stats = ctx.saved_tensors
+        dx0, dx1, dw, db = _conv_bwd_from_dconv(ctx, x0, x1, weight, dconv.contiguous(), zero_bias_grad=True, prev=(prev_conv_out, prev_stats))
+        return (dx0, dx1, dw, db, None, None, None, None, None, None, None, None, None, None)
 
 
 class _FusedHead(torch.autograd.Function):
@@ -572,7 +607,7 @@ class _FusedHead(torch.autograd.Function):
         return (dconv, None, dgamma, dbeta, dw.reshape(ctx.fw_shape), (db if ctx.has_fb else None), None, None, None, None, None, None)
 
 
-def conv_batch_stats(x0, x1, conv, bn, impl=0):
+def conv_batch_stats(x0, x1, conv, bn, impl=0, prev=None):
     """(conv_out, stats) of conv -> BatchNorm3d in training mode, the normalisation itself left to fused_head()."""
     if bn.momentum is None:
         raise ValueError("BatchNorm3d(momentum=None) (cumulative moving average) is not supported by libb200unet")
@@ -580,8 +615,9 @@ def conv_batch_stats(x0, x1, conv, bn, impl=0):
                             ("num_batches_tracked", bn.num_batches_tracked, torch.int64)):
         if buf is not None and (buf.dtype != want or not buf.is_contiguous() or not buf.is_cuda):
             raise TypeError(f"BatchNorm3d.{name} must be a contiguous CUDA {want} tensor (got {buf.dtype} on {buf.device})")
+    pco, pst = prev if prev is not None else (None, None)
     return _ConvStats.apply(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
-                            bn.eps, bn.momentum, impl)
+                            bn.eps, bn.momentum, impl, pco, pst)
 
 
 def fused_head(conv_out, stats, bn, final_conv, target, mode, alpha=0.5, beta=0.5, want_confusion=False, round_bf16=True):
@@ -590,13 +626,16 @@ def fused_head(conv_out, stats, bn, final_conv, target, mode, alpha=0.5, beta=0.
                             want_confusion, round_bf16)
 
 
-def conv_bn_act(x0, x1, conv, bn, dropmask, training, impl=0):
+def conv_bn_act(x0, x1, conv, bn, dropmask, training, impl=0, prev=None, return_ctx=False):
+    """One half of a DoubleConv.  prev = (conv_out, stats) returned (return_ctx=True) by the conv_bn_act whose output is x0."""
     if bn.momentum is None:
         # torch switches to a cumulative moving average (factor 1 / num_batches_tracked) here; the reference never does
         # (models/unet.py:12,16 use the default 0.1) and the fused finalize kernel takes a launch-constant factor
         raise ValueError("BatchNorm3d(momentum=None) (cumulative moving average) is not supported by libb200unet")
-    return _ConvBNAct.apply(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                            bn.num_batches_tracked, dropmask, training, bn.eps, bn.momentum, impl)
+    pco, pst = prev if prev is not None else (None, None)
+    y, conv_out, stats = _ConvBNAct.apply(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                          bn.num_batches_tracked, dropmask, training, bn.eps, bn.momentum, impl, pco, pst)
+    return (y, (conv_out, stats)) if return_ctx else y
 
 
 # --------------------------------------------------------------------------- MaxPool3d(2,2)

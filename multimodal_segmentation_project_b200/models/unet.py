@@ -54,11 +54,14 @@ class DoubleConv(nn.Module):
         seq = self.double_conv
         n = x0.shape[0]
         m0 = self._mask(seq[3], n, seq[0].out_channels, x0.device)
-        h = F.conv_bn_act(x0, x1, seq[0], seq[1], m0, seq[1].training, impl)
+        h, hctx = F.conv_bn_act(x0, x1, seq[0], seq[1], m0, seq[1].training, impl, return_ctx=True)
+        # without dropout h == relu(bn(conv_out)): the second conv's data-gradient kernel can then carry the first BatchNorm's
+        # backward reduction (functional._conv_bwd_from_dconv)
+        prev = hctx if (m0 is None and seq[1].training) else None
         if defer_last_norm:
-            return F.conv_batch_stats(h, None, seq[4], seq[5], impl)
+            return F.conv_batch_stats(h, None, seq[4], seq[5], impl, prev=prev)
         m1 = self._mask(seq[7], n, seq[4].out_channels, x0.device)
-        return F.conv_bn_act(h, None, seq[4], seq[5], m1, seq[5].training, impl)
+        return F.conv_bn_act(h, None, seq[4], seq[5], m1, seq[5].training, impl, prev=prev)
 
     def forward(self, x):
         """NCDHW in, NCDHW out (fp32) — the stand-alone module contract of the reference."""

@@ -743,6 +743,7 @@ def test_conv_epilogue_bn_statistics_match_separate_pass(cuda_dev, shape):
     with torch.no_grad():
         conv.bias.add_(torch.linspace(-2, 3, Cout, device="cuda"))       # |mean| >> std on some channels
     outs = []
+    F.conv_bn_act(x, None, conv, torch.nn.BatchNorm3d(Cout).cuda(), None, True)      # packs (and caches) the weights: not part of the count
     for fused in (True, False):
         F.set_fuse_bn_stats(fused)
         try:

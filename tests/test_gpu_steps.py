@@ -505,3 +505,37 @@ def test_packed_weight_cache_follows_every_kind_of_weight_update(cuda_dev):
     vnet = UNet3D(1, 4, dropout_rate=0.0).cuda(); vnet.load_state_dict(sd2); vnet.train()
     tv = DataParallelTrainer(vnet, M.combined_loss, lr=1e-3, autocast_dtype=torch.bfloat16)
     assert l4 == tv.step(xc, yc).item()
+
+
+@pytest.mark.gpu
+def test_bn_backward_reduction_rides_on_the_data_gradient_kernel(cuda_dev):
+    """models/unet.py:11-18: backward of conv -> BN -> ReLU -> conv.  The second conv's data-gradient kernel (row-streaming tcgen05,
+    top level) reduces its own output against the first conv's pre-BN tensor, so the first BatchNorm's backward needs no
+    bn_act_bwd_reduce pass.  Same gy bits, sums equal up to summation order."""
+    sd = init_state_dict(1, 4, seed=0)
+    x, y = structured_volume(2, (48, 128, 128), seed=29)
+    xc, yc = x.cuda(), y.cuda()
+
+    def run(fused):
+        F.set_fuse_bn_bwd(fused)
+        try:
+            net = UNet3D(1, 4, dropout_rate=0.0).cuda(); net.load_state_dict(sd); net.train()
+            n0 = F._lib.launch_count()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                _, loss, _ = net.forward_with_loss(xc, yc, M.combined_loss)
+            loss.backward()
+            torch.cuda.synchronize()
+            return loss.item(), {k: q.grad.clone() for k, q in net.named_parameters()}, F._lib.launch_count() - n0
+        finally:
+            F.set_fuse_bn_bwd(True)
+
+    lf, gf, nf = run(True)
+    lu, gu, nu = run(False)
+    assert lf == lu
+    assert nf <= nu - 2, (nf, nu)            # encoder.0 and decoder.3: the first conv's reduce pass is gone
+    assert not F._bnbwd_handoff               # every hand-off was consumed
+    keys = [k for k in gu if not _skip_bias(k)]
+    a = torch.cat([gf[k].flatten() for k in keys]); b = torch.cat([gu[k].flatten() for k in keys])
+    assert rel_l2(a, b) <= 1e-3, rel_l2(a, b)
+    for k in ("encoder.0.double_conv.1.weight", "encoder.0.double_conv.1.bias", "decoder.3.double_conv.1.weight", "decoder.3.double_conv.1.bias"):
+        assert rel_l2(gf[k], gu[k]) <= 5e-4, (k, rel_l2(gf[k], gu[k]))      # fp32 sums over 1.5 M voxels in two different orders
