@@ -13,9 +13,9 @@ from multimodal_segmentation_project_b200.utils import metrics as M
 dev = torch.device("cuda")
 torch.manual_seed(0)
 model = UNet3D(1, 4, dropout_rate=0.0).to(dev).train()
-tr = DataParallelTrainer(model, M.combined_loss, lr=1e-3, autocast_dtype=torch.bfloat16, metrics_fn=lambda lg, y: F.confusion_counts(lg, y))
+tr = DataParallelTrainer(model, M.combined_loss, lr=1e-3, autocast_dtype=torch.bfloat16, metrics_fn="confusion")
 x, y = structured_volume(2, 128, seed=1234)
-x, y = x.to(dev), y.to(dev)
+x, y = x.to(dev).bfloat16(), y.to(dev).to(torch.uint8)
 for _ in range(3):
     tr.step(x, y)
 torch.cuda.synchronize()
