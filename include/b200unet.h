@@ -303,6 +303,17 @@ int b200_mri_normalize(const float* x, float* y, int64_t n, const double* params
 int b200_label_remap(const int64_t* in, void* out, int64_t n, const int64_t* lo, const int64_t* hi, const int64_t* val, int nranges,
                      int out_u8, void* stream);
 
+/* ---------------------------------------------------------------- intensity augmentations (utils/dataloader.py:252-260)
+ * Device versions of the five MONAI transforms combined_transform() applies; MONAI (monai>=1.2.0) is not part of the reference
+ * tree: csrc/augment_kernels.cu restates its published array transforms.  Random draws are made by the caller. float32 [C, D, H, W]. */
+int b200_aug_bias_field(const float* x, float* y, int C, int D, int H, int W, int degree, const double* coeff, void* stream);
+int b200_aug_gaussian_noise(const float* x, const float* z, float* y, int64_t n, float mean, float std, void* stream);
+int b200_minmax_f32(const float* x, int64_t n, float* minmax, void* workspace, void* stream);
+int b200_aug_adjust_contrast(const float* x, float* y, int64_t n, const float* minmax, float gamma, void* stream);
+int b200_aug_histogram_shift(const float* x, float* y, int64_t n, const float* minmax, const double* ref, const double* floating, int ncp,
+                             void* stream);
+int b200_aug_coarse_dropout(float* img, int64_t* label, int C, int D, int H, int W, const int* holes, int nholes, float fill, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

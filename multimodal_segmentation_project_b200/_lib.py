@@ -105,6 +105,12 @@ def _declare(lib) -> None:
         "b200_linear_fwd": (I, [P, P, P, P, I, P, I, I, I, P]),
         "b200_linear_bwd": (I, [P, P, P, P, P, I, P, P, P, I, I, I, P]),
         "b200_ce_rows": (I, [P, P, I, I, P, P, P]),
+        "b200_aug_bias_field": (I, [P, P, I, I, I, I, I, P, P]),
+        "b200_aug_gaussian_noise": (I, [P, P, P, L, F, F, P]),
+        "b200_minmax_f32": (I, [P, L, P, P, P]),
+        "b200_aug_adjust_contrast": (I, [P, P, L, P, F, P]),
+        "b200_aug_histogram_shift": (I, [P, P, L, P, P, P, I, P]),
+        "b200_aug_coarse_dropout": (I, [P, P, I, I, I, I, P, I, F, P]),
         "b200_adamw_prepare": (I, [P, F, F, P, P]),
         "b200_adamw_flat": (I, [P, P, P, P, L, P, F, F, F, F, F, P]),
     }

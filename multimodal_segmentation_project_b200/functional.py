@@ -393,12 +393,15 @@ class _ConvBNAct(torch.autograd.Function):
         ctx.training = bool(training)
         ctx.has_bias = bias is not None
         ctx.mark_non_differentiable(conv_out, stats)
+        ctx.set_materialize_grads(False)      # no zero-filled gradient tensors for the two pass-through outputs
         return y, conv_out, stats
 
     @staticmethod
     def backward(ctx, gy, _gconv=None, _gstats=None):
         L = _lib.load()
         x0, x1, weight, conv_out, stats, dropmask, prev_conv_out, prev_stats = ctx.saved_tensors
+        if gy is None:                        # (materialize_grads is off) nothing flows back through this block
+            return (None,) * 16
         gy = gy.contiguous()
         N, D, H, W, Cout = conv_out.shape
         M, S = N * D * H * W, D * H * W
@@ -533,11 +536,14 @@ class _ConvStats(torch.autograd.Function):
         ctx.save_for_backward(x0, x1, weight, prev_conv_out, prev_stats)
         ctx.has_bias = bias is not None
         ctx.mark_non_differentiable(stats)
+        ctx.set_materialize_grads(False)
         return conv_out, stats
 
     @staticmethod
     def backward(ctx, dconv, _gstats):
         x0, x1, weight, prev_conv_out, prev_stats = ctx.saved_tensors
+        if dconv is None:
+            return (None,) * 14
         dx0, dx1, dw, db = _conv_bwd_from_dconv(ctx, x0, x1, weight, dconv.contiguous(), zero_bias_grad=True, prev=(prev_conv_out, prev_stats))
         return (dx0, dx1, dw, db, None, None, None, None, None, None, None, None, None, None)
 
@@ -577,12 +583,15 @@ class _FusedHead(torch.autograd.Function):
         ctx.mark_non_differentiable(logits)
         if conf is not None:
             ctx.mark_non_differentiable(conf)
+        ctx.set_materialize_grads(False)
         return loss, logits, conf
 
     @staticmethod
     def backward(ctx, gloss, _glogits, _gconf):
         L = _lib.load()
         conv_out, stats, w32, logits, y, coef = ctx.saved_tensors
+        if gloss is None:
+            return (None,) * 12
         N, D, H, W, Cin = conv_out.shape
         C = w32.shape[0]
         S = D * H * W
