@@ -1,9 +1,10 @@
 // partial_reduce.cuh — fixed-order (deterministic) reduction of per-CTA split-K partials.
 //
-// partial[group][cta < spatial][e < stride] -> out[map(group, e)].  A block covers 256 / LANES consecutive source elements
-// times LANES partial-lanes: for a fixed lane the block's threads read consecutive floats (whole 32-byte sectors), lane l
-// sums partials l, l + LANES, ... in fp64, and thread lane 0 adds the LANES lane sums in ascending order.  The previous
-// one-warp-per-output kernels read one float per 32-byte sector (8x read amplification, 13 us per layer).
+// partial[group][cta < spatial][e < stride] -> out[map(group, e)].  A block covers EPB = 256 / LANES consecutive source elements
+// times LANES partial-lanes: lane l sums partials l, l + LANES, ... in fp64 (four loads in flight), then thread lane 0 adds the
+// LANES lane sums in ascending order.  With many partials LANES = 8 and EPB = 32: every warp-load is one whole 128-byte line of
+// one partial row and a launch has stride / 32 fat blocks.  (Round 1: LANES = 32, EPB = 8 -> 32-byte pieces and 4x the blocks,
+// 15 us per layer for a 14 MB read; before that one warp per output element with 8x read amplification.)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -19,8 +20,13 @@ partial_reduce_kernel(const float* __restrict__ partial, int spatial, int64_t st
   double s = 0.0;
   if (e < stride) {
     const float* src = partial + (int64_t)group * spatial * stride + e;
-#pragma unroll 4
-    for (int c = l; c < spatial; c += lanes) s += (double)src[(int64_t)c * stride];
+    int c = l;
+    for (; c + 3 * lanes < spatial; c += 4 * lanes) {      // four independent loads in flight, summed in ascending order
+      const float v0 = __ldcs(src + (int64_t)c * stride), v1 = __ldcs(src + (int64_t)(c + lanes) * stride);
+      const float v2 = __ldcs(src + (int64_t)(c + 2 * lanes) * stride), v3 = __ldcs(src + (int64_t)(c + 3 * lanes) * stride);
+      s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
+    }
+    for (; c < spatial; c += lanes) s += (double)__ldcs(src + (int64_t)c * stride);
   }
   sm[threadIdx.x] = s;
   __syncthreads();
@@ -33,7 +39,8 @@ partial_reduce_kernel(const float* __restrict__ partial, int spatial, int64_t st
 
 template <typename MapF>
 inline cudaError_t launch_partial_reduce(const float* partial, int spatial, int64_t stride, int groups, MapF map, float* out, cudaStream_t stream) {
-  const int lanes = spatial >= 64 ? 32 : 1;  // few partials: one thread per output, consecutive threads read consecutive floats
+  // few partials: one thread per output, consecutive threads read consecutive floats
+  const int lanes = spatial >= 16 ? 8 : 1;
   const int epb = 256 / lanes;
   dim3 grid((unsigned)((stride + epb - 1) / epb), (unsigned)groups);
   partial_reduce_kernel<<<grid, 256, 0, stream>>>(partial, spatial, stride, lanes, map, out);
