@@ -26,15 +26,38 @@ import torch.distributed as dist
 
 
 class FlatParams:
-    """Re-homes a module's parameters and gradients into two flat fp32 buffers."""
+    """Re-homes a module's parameters and gradients into two flat fp32 buffers.
 
-    def __init__(self, module: torch.nn.Module, early_prefixes=("final_conv", "decoder", "upconvs", "bottleneck")):
+    Parameters are laid out bucket by bucket in the order their gradients COMPLETE during backward: bucket 0 = the parameter-heavy
+    tail of the forward pass (final conv, decoder, up-convs, bottleneck: 83 % of the U-Net's parameters), then groups of encoder
+    levels from the deepest up.  Bucket i is final when backward reaches the first layer of the next group: that layer's
+    second-conv weight is the bucket's SENTINEL (a post-accumulate-grad hook on it starts the bucket's all-reduce on a side
+    stream).  Only the last, small bucket (the two top encoder levels: 0.2 MB for the default U-Net) is reduced after backward."""
+
+    def __init__(self, module: torch.nn.Module, early_prefixes=("final_conv", "decoder", "upconvs", "bottleneck"), late_levels_per_bucket=2):
         params = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
-        # bucket 0 ("early"): gradients that are complete well before backward ends
         early = [(n, p) for n, p in params if n.startswith(tuple(early_prefixes))]
-        late = [(n, p) for n, p in params if not n.startswith(tuple(early_prefixes))]
-        self.order = early + late
-        self.n_early = sum(p.numel() for _, p in early)
+        rest = [(n, p) for n, p in params if not n.startswith(tuple(early_prefixes))]
+        enc_ids = sorted({int(n.split(".")[1]) for n, _ in rest if n.startswith("encoder.") and n.split(".")[1].isdigit()}, reverse=True)
+        groups = [early] if early else []
+        # encoder levels, deepest first, `late_levels_per_bucket` levels per bucket; anything else trainable goes last
+        covered = set()
+        for i in range(0, len(enc_ids), max(1, late_levels_per_bucket)):
+            ids = enc_ids[i:i + max(1, late_levels_per_bucket)]
+            grp = [(n, p) for n, p in rest if any(n.startswith(f"encoder.{j}.") for j in ids)]
+            covered |= {n for n, _ in grp}
+            if grp:
+                groups.append(grp)
+        other = [(n, p) for n, p in rest if n not in covered]
+        if other:
+            if len(groups) > (1 if early else 0):
+                groups[-1] = groups[-1] + other
+            else:
+                groups.append(other)
+        if not groups:
+            raise ValueError("FlatParams: the module has no trainable parameters")
+        self.groups = groups
+        self.order = [np_ for g in groups for np_ in g]
         total = sum(p.numel() for _, p in self.order)
         # pad so that the fused optimiser can use 128-bit accesses
         self.total = (total + 3) // 4 * 4
@@ -50,24 +73,38 @@ class FlatParams:
             p.grad = self.grad[off:off + k].view_as(p)
             self.offsets[n] = (off, k)
             off += k
-        # Sentinel = a parameter of the autograd node that runs right AFTER the early bucket is complete:
-        # the second conv of the deepest encoder block.  AccumulateGrad nodes run with top priority, so
-        # when this one fires every gradient of the bottleneck / decoder / upconvs / final conv is final.
-        self.early_sentinel = None
-        if early and late:
-            enc_ids = sorted({int(n.split(".")[1]) for n, _ in late if n.startswith("encoder.")})
-            if enc_ids:
-                want = f"encoder.{enc_ids[-1]}.double_conv.4.weight"
-                cands = [p for n, p in late if n == want]
-                self.early_sentinel = cands[0] if cands else None
-
+        # element / parameter-count boundaries of the buckets
+        self.bucket_elems, self.bucket_params = [0], [0]
+        for g in groups:
+            self.bucket_elems.append(self.bucket_elems[-1] + sum(p.numel() for _, p in g))
+            self.bucket_params.append(self.bucket_params[-1] + len(g))
+        self.bucket_elems[-1] = self.total       # the padding rides with the last bucket
+        # Sentinel of bucket i (i < last) = a parameter of the autograd node that runs right AFTER the bucket is complete: the second
+        # conv of the deepest encoder level of the NEXT group.  AccumulateGrad nodes run with top priority, so when it fires every
+        # gradient of the earlier buckets is final.
+        self.sentinels = []
+        for i in range(len(groups) - 1):
+            nxt = groups[i + 1]
+            ids = sorted({int(n.split(".")[1]) for n, _ in nxt if n.startswith("encoder.") and n.split(".")[1].isdigit()}, reverse=True)
+            cand = [p for n, p in nxt if ids and n == f"encoder.{ids[0]}.double_conv.4.weight"]
+            self.sentinels.append(cand[0] if cand else None)
+        if any(s_ is None for s_ in self.sentinels):      # unknown layout: fall back to a single bucket reduced after backward
+            self.sentinels = []
+            self.bucket_elems, self.bucket_params = [0, self.total], [0, len(self.order)]
+        self.n_early = self.bucket_elems[1] if len(self.bucket_elems) > 2 else (self.bucket_elems[1] if early and rest else (self.total if early else 0))
+        self.early_sentinel = self.sentinels[0] if self.sentinels else None
         self._views = [self.grad[o:o + k].view_as(p) for (n, p), (o, k) in zip(self.order, (self.offsets[n] for n, _ in self.order))]
-        self.n_early_params = len(early)
+        self.n_early_params = self.bucket_params[1] if len(self.bucket_params) > 2 else len(self.order)
+
+    @property
+    def n_buckets(self):
+        return len(self.bucket_elems) - 1
+
+    def bucket(self, i):
+        return self.grad[self.bucket_elems[i]:self.bucket_elems[i + 1]]
 
     def buckets(self):
-        if self.n_early in (0, self.total):
-            return [self.grad]
-        return [self.grad[: self.n_early], self.grad[self.n_early:]]
+        return [self.bucket(i) for i in range(self.n_buckets)]
 
     def zero_grad(self):
         self.grad.zero_()
@@ -79,12 +116,19 @@ class FlatParams:
         for _, p in self.order:
             p.grad = None
 
+    def gather_bucket(self, i, accumulate=False):
+        """copies the detached gradients of bucket i into the flat buffer"""
+        self._gather_range(self.bucket_params[i], self.bucket_params[i + 1], accumulate)
+
     def gather_grads(self, which="all", accumulate=False):
         # A parameter that received no gradient this step gets a ZERO slice: FlatAdamW then still applies weight decay and
         # decays its moments, whereas torch.optim.AdamW (the reference's optimiser) skips `grad is None` parameters.  Every
         # parameter of UNet3D / the DANN variant receives a gradient on every step, so the two agree on the path this
         # library covers; modules with conditionally unused parameters must not rely on the skip.
         lo, hi = {"all": (0, len(self.order)), "early": (0, self.n_early_params), "late": (self.n_early_params, len(self.order))}[which]
+        self._gather_range(lo, hi, accumulate)
+
+    def _gather_range(self, lo, hi, accumulate=False):
         dst, src = [], []
         for (n, p), v in zip(self.order[lo:hi], self._views[lo:hi]):
             if p.grad is None:
@@ -135,14 +179,15 @@ class DataParallelTrainer:
             named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]  # model.parameters() order = torch.optim's
             self.opt = FlatAdamW(self.fp.flat, self.fp.grad, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
                                  named_params=named, offsets=self.fp.offsets)
-        self.overlap = overlap and self.world > 1 and dev.type == "cuda" and self.fp.early_sentinel is not None
+        self.overlap = overlap and self.world > 1 and dev.type == "cuda" and len(self.fp.sentinels) > 0
         self._side = torch.cuda.Stream(device=dev) if self.overlap else None
         # weight gradients run on a side stream and are joined at the end of backward / before a bucket is gathered:
         # safe here because step() detaches the gradients first (autograd stores, never accumulates)
         self._defer_wgrad = dev.type == "cuda" and os.environ.get("B200_DEFER_WGRAD_JOIN", "1") != "0"
-        self._early_done = False
+        self._buckets_done = 0      # buckets whose all-reduce has been launched during the running backward pass
         if self.overlap:
-            self.fp.early_sentinel.register_post_accumulate_grad_hook(self._early_hook)
+            for i, sentinel in enumerate(self.fp.sentinels):
+                sentinel.register_post_accumulate_grad_hook(lambda _p, i=i: self._bucket_hook(i))
         # gradient accumulation (accelerator.accumulate, train_unet.py:221): micro-steps 1..k-1 only add their gradients
         # (of loss / k) into the flat buffer; the k-th also all-reduces and steps the optimiser
         self.accum = max(1, int(accumulation_steps))
@@ -173,18 +218,18 @@ class DataParallelTrainer:
                     b.copy_(flat[off:off + b.numel()].view_as(b))
                     off += b.numel()
 
-    def _early_hook(self, _param):
-        # called by autograd right after the sentinel's gradient was accumulated: everything in the
-        # early bucket is final -> reduce it on the side stream while the encoder backward continues
-        if self.accum > 1:
+    def _bucket_hook(self, i):
+        # called by autograd right after sentinel i's gradient was accumulated: every gradient of bucket i is final -> reduce it on
+        # the side stream while the rest of the backward pass continues
+        if self.accum > 1 or i != self._buckets_done:
             return  # accumulating: buckets are reduced once, after the last micro-step
         self._join_wgrads()
-        self.fp.gather_grads("early")
+        self.fp.gather_bucket(i)
         cur = torch.cuda.current_stream()
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
-            dist.all_reduce(self.fp.buckets()[0], op=dist.ReduceOp.SUM, group=self.pg)
-        self._early_done = True
+            dist.all_reduce(self.fp.bucket(i), op=dist.ReduceOp.SUM, group=self.pg)
+        self._buckets_done = i + 1
 
     def _join_wgrads(self):
         if self._defer_wgrad:
@@ -193,21 +238,15 @@ class DataParallelTrainer:
 
     def allreduce_grads(self):
         self._join_wgrads()
-        if self.overlap and self._early_done:
-            self.fp.gather_grads("late")
-        else:
-            self.fp.gather_grads("all")
-        if self.world == 1:
-            self._early_done = False
-            return
-        b = self.fp.buckets()
-        if self.overlap and self._early_done:
-            dist.all_reduce(b[-1], op=dist.ReduceOp.SUM, group=self.pg)
-            torch.cuda.current_stream().wait_stream(self._side)
-        else:
-            for t in b:
-                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
-        self._early_done = False
+        done = self._buckets_done if self.overlap else 0
+        for i in range(done, self.fp.n_buckets):
+            self.fp.gather_bucket(i)
+        if self.world > 1:
+            for i in range(done, self.fp.n_buckets):
+                dist.all_reduce(self.fp.bucket(i), op=dist.ReduceOp.SUM, group=self.pg)
+            if done:
+                torch.cuda.current_stream().wait_stream(self._side)
+        self._buckets_done = 0
 
     # -- one training step -------------------------------------------------------------------------
     def _step_impl(self, x, y):

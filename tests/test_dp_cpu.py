@@ -99,11 +99,16 @@ def test_flat_params_layout_and_buckets():
     lo, hi = fp.flat.data_ptr(), fp.flat.data_ptr() + fp.flat.numel() * 4
     for _, p in net.named_parameters():
         assert lo <= p.data_ptr() < hi and p.grad is not None and p.grad.shape == p.shape
-    # early bucket = final conv + decoder + upconvs + bottleneck: the parameter-heavy, FLOP-light layers
+    # bucket 0 = final conv + decoder + upconvs + bottleneck: the parameter-heavy, FLOP-light layers; then encoder levels 3+2
+    # (reduced under the level-1/0 backward) and 1+0 (0.2 MB: the only all-reduce left after backward)
     b = fp.buckets()
-    assert len(b) == 2 and 0.80 < b[0].numel() / 5647908 < 0.90
+    assert len(b) == 3 and 0.80 < b[0].numel() / 5647908 < 0.90
+    assert sum(t.numel() for t in b) == fp.total and b[2].numel() * 4 < 0.25 * 2 ** 20
     names = dict(net.named_parameters())
     assert fp.early_sentinel is names["encoder.3.double_conv.4.weight"]
+    assert fp.sentinels == [names["encoder.3.double_conv.4.weight"], names["encoder.1.double_conv.4.weight"]]
+    assert [n for n, _ in fp.order[fp.bucket_params[1]:fp.bucket_params[2]]][0].startswith("encoder.")
+    assert all(n.startswith(("encoder.0.", "encoder.1.")) for n, _ in fp.order[fp.bucket_params[2]:])
     # writing through the flat buffer is visible in the module (what the fused optimiser relies on)
     fp.flat.zero_()
     assert float(net.final_conv.weight.detach().abs().sum()) == 0.0
@@ -112,7 +117,7 @@ def test_flat_params_layout_and_buckets():
     for p in net2.encoder.parameters():
         p.requires_grad = False
     fp2 = FlatParams(net2)
-    assert fp2.early_sentinel is None and len(fp2.buckets()) == 1
+    assert fp2.early_sentinel is None and len(fp2.buckets()) == 1 and fp2.sentinels == []
 
 
 def _accum_worker(rank, world, port, out):

@@ -430,9 +430,10 @@ def test_unet_dann_variant_vs_reference_golden(cuda_dev, golden_dir):
 
 
 def test_unet_bf16_vs_cuda_autocast_oracle(cuda_dev):
-    """bf16 tolerance protocol of SURVEY.md §8d / App. F: compare against the oracle run on the GPU
-    under bf16 autocast (same rounding points), structured problem, global norms, <= 1e-2 + the
-    'no worse than 1.5x the oracle's own bf16-vs-fp32 error' criterion."""
+    """bf16 tolerance of north_star (rel. L2 <= 1e-2) against the oracle run on the GPU under bf16 autocast (same rounding points),
+    structured problem, global norms — each quantity asserted by name — plus App. F's sanity bound: no further from the fp32
+    truth than 1.25x the reference's own bf16 path.  Measured on B200 (profiles/r02_parity_measured.jsonl): logits 4.9e-3,
+    gradients 6.7e-3 against the bf16 oracle; the oracle's own bf16-vs-fp32 distance is 4.7e-3 / 7.9e-3."""
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     sd = init_state_dict(1, 4, seed=0)
@@ -464,8 +465,12 @@ def test_unet_bf16_vs_cuda_autocast_oracle(cuda_dev):
     oracle_self = rel_l2(z16, z32)
     print(f"logits: ours-vs-bf16oracle {rel_l2(logits, z16):.3e} ours-vs-fp32 {rel_l2(logits, z32):.3e} oracle16-vs-32 {oracle_self:.3e}")
     print(f"grads : ours-vs-bf16oracle {rel_l2(ours, r16):.3e} ours-vs-fp32 {rel_l2(ours, r32):.3e} oracle16-vs-32 {rel_l2(r16, r32):.3e}")
-    assert rel_l2(logits, z16) <= 1e-2 or rel_l2(logits, z32) <= 1.5 * oracle_self
-    assert rel_l2(ours, r16) <= 1e-2 or rel_l2(ours, r32) <= 1.5 * rel_l2(r16, r32)
+    logits_vs_bf16, grads_vs_bf16 = rel_l2(logits, z16), rel_l2(ours, r16)
+    logits_vs_fp32, grads_vs_fp32 = rel_l2(logits, z32), rel_l2(ours, r32)
+    assert logits_vs_bf16 <= 1e-2, logits_vs_bf16
+    assert grads_vs_bf16 <= 1e-2, grads_vs_bf16
+    assert logits_vs_fp32 <= 1.25 * oracle_self + 1e-3, (logits_vs_fp32, oracle_self)
+    assert grads_vs_fp32 <= 1.25 * rel_l2(r16, r32) + 1e-3, (grads_vs_fp32, rel_l2(r16, r32))
     assert abs(loss.item() - l16.item()) <= 1e-2 * abs(l16.item())
     # argmax agreement with the bf16 oracle
     agree = (logits.argmax(1) == z16.argmax(1)).float().mean().item()
