@@ -134,6 +134,10 @@ int64_t b200_conv3d_wgrad_workspace(int c0, int c1, int Cout, int N, int D, int 
 /* process-wide selection of the weight-gradient kernel: 0 auto (tcgen05 for bf16 when the channel
  * counts allow), 1 CUDA-core split-K, 2 tcgen05 (error if unsupported) — for tests and benchmarks. */
 int b200_set_wgrad_impl(int impl);
+/* voxel-pair tcgen05 weight gradient for the 16-channel layers (wgrad_tc4.cu): on = 0 falls back to the M = 64 kernel
+ * (wgrad_tc2.cu); dseg > 0 forces the d-run per CTA, 0 = planned — for tests and A/B timing.  Workspace sizes depend on
+ * these settings: change them only between calls of b200_conv3d_wgrad_workspace / b200_conv3d_wgrad pairs. */
+int b200_set_wgrad_pair(int on, int dseg);
 /* test hook: the next wide-row tcgen05 weight gradient returns B200_ERR_UNSUPPORTED without launching (checks that a
  * failing kernel selection surfaces as an error instead of an uninitialised dw). */
 int b200_debug_fail_next_wgrad(int on);

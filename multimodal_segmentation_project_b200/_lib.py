@@ -58,6 +58,7 @@ def _declare(lib) -> None:
         "b200_conv3d_k3_bnbwd": (I, [I, I, P, I, P, P, I, I, I, I, I, P, P, P, P, P, P, P]),
         "b200_conv3d_wgrad_workspace": (L, [I, I, I, I, I, I, I]),
         "b200_set_wgrad_impl": (I, [I]),
+        "b200_set_wgrad_pair": (I, [I, I]),
         "b200_debug_fail_next_wgrad": (I, [I]),
         "b200_conv3d_wgrad": (I, [I, P, I, P, I, P, I, P, P, P, L, I, I, I, I, P]),
         "b200_bn_partials_bytes": (L, [I]),

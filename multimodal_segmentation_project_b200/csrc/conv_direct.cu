@@ -568,6 +568,11 @@ bool b200_conv3d_wgrad_tc3_supported(int c0, int c1, int Cout, int N, int D, int
 int64_t b200_conv3d_wgrad_tc3_workspace(int c0, int c1, int Cout, int N, int D, int H, int W);
 int b200_conv3d_wgrad_tc3(const void* x0, int c0, const void* x1, int c1, const void* dy, int Cout, float* dw, void* workspace,
                           int N, int D, int H, int W, cudaStream_t stream);
+// voxel-pair variant (wgrad_tc4.cu): 16-channel tensors, operand rows = two w-adjacent voxels (B200_WGRAD_PAIR=0 disables it)
+bool b200_conv3d_wgrad_tc4_supported(int c0, int c1, int Cout, int N, int D, int H, int W);
+int64_t b200_conv3d_wgrad_tc4_workspace(int c0, int c1, int Cout, int N, int D, int H, int W);
+int b200_conv3d_wgrad_tc4(const void* x0, int c0, const void* x1, int c1, const void* dy, int Cout, float* dw, void* workspace,
+                          int N, int D, int H, int W, cudaStream_t stream);
 static int g_wgrad_impl = 0;  // 0 auto, 1 CUDA-core, 2 tcgen05
 static int g_inject_wgrad_failure = 0;  // tests: the next wide-row tcgen05 weight gradient reports failure
 // in_channels == 1 first layer (conv_stem.cu)
@@ -749,6 +754,10 @@ extern "C" int64_t b200_conv3d_wgrad_workspace(int c0, int c1, int Cout, int N, 
     const int64_t t = b200_conv3d_wgrad_tc3_workspace(c0, c1, Cout, N, D, H, W);
     if (t > main_bytes) main_bytes = t;
   }
+  if (b200_conv3d_wgrad_tc4_supported(c0, c1, Cout, N, D, H, W)) {
+    const int64_t t = b200_conv3d_wgrad_tc4_workspace(c0, c1, Cout, N, D, H, W);
+    if (t > main_bytes) main_bytes = t;
+  }
   if (b200_conv_stem_wgrad_supported(c0, c1, Cout) && b200_conv_stem_wgrad_workspace(Cout) > main_bytes)
     main_bytes = b200_conv_stem_wgrad_workspace(Cout);
   return b200_bn_partials_bytes(((Cout + 7) / 8) * 8) + main_bytes;
@@ -769,6 +778,8 @@ extern "C" int b200_conv3d_wgrad(int dtype, const void* x0, int c0, const void* 
   // v2 (kw on M, kh on N) wins while the channel counts are small; for wide layers v1 fills its 64 M rows with real channels
   const bool use_v3 = dtype == B200_BF16 && wg_version() >= 2 && wg_wide_enabled() && b200_conv3d_wgrad_tc3_supported(c0, c1, Cout, N, D, H, W);
   const bool use_v2 = wg_version() == 2 && (int64_t)(c0 + c1) * Cout <= 4096 && b200_conv3d_wgrad_tc2_supported(c0, c1, Cout, N, D, H, W);
+  // 16-channel layers: the voxel-pair kernel (M = 128 x N = 64 instructions, 56 % of the blocks useful) replaces v2 (M = 64 x N = 48)
+  const bool use_v4 = dtype == B200_BF16 && use_v2 && !use_v3 && b200_conv3d_wgrad_tc4_supported(c0, c1, Cout, N, D, H, W);
   const bool tc_ok = dtype == B200_BF16 && (use_v2 ? b200_conv3d_wgrad_tc2_supported(c0, c1, Cout, N, D, H, W)
                                                    : b200_conv3d_wgrad_tc_supported(c0, c1, Cout, N, D, H, W));
   B200_REQUIRE(g_wgrad_impl != 2 || tc_ok, B200_ERR_UNSUPPORTED, "conv3d_wgrad: tcgen05 path forced but unsupported for this problem");
@@ -779,6 +790,9 @@ extern "C" int b200_conv3d_wgrad(int dtype, const void* x0, int c0, const void* 
   } else if (use_v3 && g_wgrad_impl != 1) {
     rc = g_inject_wgrad_failure ? (g_inject_wgrad_failure = 0, b200_set_error("conv3d_wgrad: injected failure (b200_debug_fail_next_wgrad)"), B200_ERR_UNSUPPORTED)
                                 : b200_conv3d_wgrad_tc3(x0, c0, x1, c1, dy, Cout, dw, partial, N, D, H, W, st);
+    if (rc) return rc;
+  } else if (use_v4 && g_wgrad_impl != 1) {
+    rc = b200_conv3d_wgrad_tc4(x0, c0, x1, c1, dy, Cout, dw, partial, N, D, H, W, st);
     if (rc) return rc;
   } else if (tc_ok && g_wgrad_impl != 1) {
     rc = use_v2 ? b200_conv3d_wgrad_tc2(x0, c0, x1, c1, dy, Cout, dw, partial, N, D, H, W, st)

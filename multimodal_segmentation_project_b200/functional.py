@@ -303,6 +303,11 @@ def set_wgrad_impl(impl: int) -> None:
     check(_lib.load().b200_set_wgrad_impl(int(impl)), "set_wgrad_impl")
 
 
+def set_wgrad_pair(on: bool, dseg: int = 0) -> None:
+    """Voxel-pair tcgen05 weight gradient for the 16-channel layers (default on); dseg > 0 forces the d-run per CTA (tests, A/B timing)."""
+    check(_lib.load().b200_set_wgrad_pair(int(bool(on)), int(dseg)), "set_wgrad_pair")
+
+
 def set_conv_persistent(mode: int) -> None:
     """0 never, 1 auto (every layer with enough tiles), 2 same as 1, 3 only 16->16 layers (process-wide; tests and benchmarks)."""
     check(_lib.load().b200_set_conv_persistent(int(mode)), "set_conv_persistent")

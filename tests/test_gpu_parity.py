@@ -675,6 +675,51 @@ def test_conv3d_wgrad_tcgen05_vs_oracle(cuda_dev, case):
     assert rel_l2(db, gy.double().sum(dim=(0, 2, 3, 4))) <= 2e-5
 
 
+WG_PAIR_CASES = [
+    # N, D, H, W, c0, c1, forced d-run per CTA (0 = planned); Cout = 16
+    (1, 8, 16, 32, 16, 0, 0),
+    (1, 12, 16, 16, 16, 16, 12),    # concat input; one CTA streams 14 X planes (both operand rings wrap), half-empty tile
+    (2, 11, 20, 40, 16, 16, 3),     # ragged tiles in h and w, two w tiles, 4 d-blocks (the last one short), two samples
+    (1, 19, 33, 18, 16, 0, 8),
+    (1, 6, 12, 64, 16, 0, 2),
+    (1, 1, 16, 16, 16, 0, 0),       # a single plane
+]
+
+
+@pytest.mark.parametrize("case", WG_PAIR_CASES)
+def test_conv3d_wgrad_plane_pairs_vs_oracle(cuda_dev, case):
+    """wgrad_tc4.cu (operand rows = pairs of w-adjacent voxels, M = 128 x N = 64 instructions) against the fp64 oracle and against the
+    M = 64 kernel it replaces (wgrad_tc2.cu): same products, fp32 accumulation in a different order."""
+    N, D, H, W, c0, c1, dseg = case
+    Cout = 16
+    Cin = c0 + c1
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(N, Cin, D, H, W, generator=gen).bfloat16().float()
+    gy = torch.randn(N, Cout, D, H, W, generator=gen).bfloat16().float()
+    w = torch.zeros(Cout, Cin, 3, 3, 3, dtype=torch.float64, requires_grad=True)
+    TF.conv3d(x.double(), w, None, padding=1).backward(gy.double())
+    x0 = cl(x[:, :c0], torch.bfloat16)
+    x1 = cl(x[:, c0:], torch.bfloat16) if c1 else None
+    dy = cl(gy, torch.bfloat16)
+    try:
+        F.set_wgrad_impl(2)
+        F.set_wgrad_pair(True, dseg)
+        n0 = _lib.launch_count()
+        dw, _ = F.conv3d_wgrad_raw(x0, x1, dy, want_bias=False)
+        dw_again, _ = F.conv3d_wgrad_raw(x0, x1, dy, want_bias=False)
+        torch.cuda.synchronize()
+        F.set_wgrad_pair(False)
+        dw_v2, _ = F.conv3d_wgrad_raw(x0, x1, dy, want_bias=False)
+        torch.cuda.synchronize()
+    finally:
+        F.set_wgrad_pair(True, 0)
+        F.set_wgrad_impl(0)
+    assert _lib.launch_count() > n0
+    assert rel_l2(dw, w.grad) <= 2e-5
+    assert torch.equal(dw, dw_again)            # fixed-order reduction: run-to-run bitwise identical
+    assert rel_l2(dw, dw_v2.double()) <= 2e-6
+
+
 # ----------------------------------------------------------------------------- binary helpers (a13)
 BINARY_CASES = ["a", "b", "c", "empty_target", "full_target"]
 
