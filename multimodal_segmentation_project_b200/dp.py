@@ -94,6 +94,9 @@ class FlatParams:
         self.n_early = self.bucket_elems[1] if len(self.bucket_elems) > 2 else (self.bucket_elems[1] if early and rest else (self.total if early else 0))
         self.early_sentinel = self.sentinels[0] if self.sentinels else None
         self._views = [self.grad[o:o + k].view_as(p) for (n, p), (o, k) in zip(self.order, (self.offsets[n] for n, _ in self.order))]
+        # gradient sinks (functional.begin_grad_sinks): parameter data pointer -> its slice of the flat gradient buffer
+        self.sinks = {p.data_ptr(): v for (_, p), v in zip(self.order, self._views)}
+        self._known_zero = set()     # indices of slices that hold zeros and that nobody writes (parameters without a gradient)
         self.n_early_params = self.bucket_params[1] if len(self.bucket_params) > 2 else len(self.order)
 
     @property
@@ -108,6 +111,7 @@ class FlatParams:
 
     def zero_grad(self):
         self.grad.zero_()
+        self._known_zero = set(range(len(self.order)))
 
     # ---- "detached gradient" mode: autograd stores every parameter gradient as its own tensor (p.grad starts as
     # None, so AccumulateGrad keeps the tensor the kernels produced instead of launching one add per parameter), and the
@@ -115,6 +119,12 @@ class FlatParams:
     def detach_grads(self):
         for _, p in self.order:
             p.grad = None
+
+    def attach_grads(self):
+        """after a step: parameters whose gradient lives only in the flat buffer show it as .grad again"""
+        for (_, p), v in zip(self.order, self._views):
+            if p.grad is None:
+                p.grad = v
 
     def gather_bucket(self, i, accumulate=False):
         """copies the detached gradients of bucket i into the flat buffer"""
@@ -129,12 +139,19 @@ class FlatParams:
         self._gather_range(lo, hi, accumulate)
 
     def _gather_range(self, lo, hi, accumulate=False):
+        from .functional import grad_was_sunk
         dst, src = [], []
-        for (n, p), v in zip(self.order[lo:hi], self._views[lo:hi]):
+        for i, ((n, p), v) in enumerate(zip(self.order[lo:hi], self._views[lo:hi]), start=lo):
             if p.grad is None:
-                if not accumulate:
+                if grad_was_sunk(p.data_ptr()):
+                    self._known_zero.discard(i)       # the backward kernels wrote this slice in place
+                elif not accumulate and i not in self._known_zero:
+                    # no gradient this step (e.g. a conv bias in front of a batch-statistics BatchNorm): the slice is zeroed once
+                    # and stays zero — all-reduce sums zeros, the optimiser only reads
                     v.zero_()
+                    self._known_zero.add(i)
             else:
+                self._known_zero.discard(i)
                 dst.append(v)
                 src.append(p.grad)
         if dst:
@@ -184,6 +201,8 @@ class DataParallelTrainer:
         # weight gradients run on a side stream and are joined at the end of backward / before a bucket is gathered:
         # safe here because step() detaches the gradients first (autograd stores, never accumulates)
         self._defer_wgrad = dev.type == "cuda" and os.environ.get("B200_DEFER_WGRAD_JOIN", "1") != "0"
+        self._grad_sinks_on = os.environ.get("B200_GRAD_SINKS", "1") != "0"
+        self._one = None
         self._buckets_done = 0      # buckets whose all-reduce has been launched during the running backward pass
         if self.overlap:
             for i, sentinel in enumerate(self.fp.sentinels):
@@ -280,10 +299,25 @@ class DataParallelTrainer:
             logits = out[0] if isinstance(out, tuple) else out
             loss = self.loss_fn(logits.float(), y if y.dtype == torch.int64 else y.long())
         if self.accum == 1:
-            loss.backward()
-            self.allreduce_grads()
+            from . import functional as F
+            use_sinks = self.fp.flat.is_cuda and self._grad_sinks_on
+            if use_sinks:
+                # parameter gradients are written straight into the flat buffer by the backward kernels; the bucket all-reduces
+                # are triggered when the backward of the first node AFTER a bucket starts
+                cbs = {s_.data_ptr(): (lambda i=i: self._bucket_hook(i)) for i, s_ in enumerate(self.fp.sentinels)} if self.overlap else None
+                F.begin_grad_sinks(self.fp.sinks, cbs)
+            try:
+                # a persistent seed gradient: autograd's own ones_like(loss) would be one more fill kernel per step
+                if self._one is None or self._one.device != loss.device or self._one.dtype != loss.dtype:
+                    self._one = torch.ones_like(loss)
+                loss.backward(gradient=self._one)
+                self.allreduce_grads()
+            finally:
+                if use_sinks:
+                    F.end_grad_sinks()
             self.opt.step(grad_scale=1.0 / self.world)
             self._repack()
+            self.fp.attach_grads()
         else:
             (loss / self.accum).backward()
             self._join_wgrads()

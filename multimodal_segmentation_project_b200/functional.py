@@ -10,6 +10,7 @@ test infrastructure and is never imported from here).
 from __future__ import annotations
 
 import ctypes
+import math
 import os
 import weakref
 
@@ -223,9 +224,55 @@ def conv3d_k3_raw(x0, x1, wpack, bias, co0, co1=0, impl=1):
     return y0, y1
 
 
-def conv3d_wgrad_raw(x0, x1, dy, want_bias=True, side=None):
+# Gradient sinks (train_unet.py:226): a trainer that keeps all gradients in one flat fp32 buffer (dp.FlatParams)
+# registers, per parameter, the slice that belongs to it.  The backward functions below then hand that slice to their kernels as
+# the destination of the parameter gradient and return None for the input, so autograd neither stores nor copies anything: no
+# per-parameter gradient tensors, no multi-tensor gather, no zero fills in the step.  Keys are parameter data pointers (the
+# tensors autograd hands back in ctx.saved_tensors are the parameters' storage, whatever Python object wraps them).
+_grad_sinks = {}       # param.data_ptr() -> fp32 view (parameter shape) of the flat gradient buffer
+_sunk = set()          # data pointers whose gradient was written to its sink since the last begin_grad_sinks()
+_bwd_callbacks = {}    # param.data_ptr() -> callable, run when the backward of the node owning that parameter starts
+
+
+def begin_grad_sinks(sinks, callbacks=None) -> None:
+    """Activates `sinks` ({param.data_ptr(): flat-gradient view}) for the backward passes that follow; `callbacks` maps a
+    parameter's data pointer to a function called at the START of the backward of the node that owns it (every node that ran
+    before it has launched its gradient kernels: what DDP's bucket-ready hooks observe, train_unet.py:384)."""
+    global _grad_sinks, _bwd_callbacks
+    _grad_sinks = sinks
+    _bwd_callbacks = callbacks or {}
+    _sunk.clear()
+
+
+def end_grad_sinks() -> None:
+    global _grad_sinks, _bwd_callbacks
+    _grad_sinks = {}
+    _bwd_callbacks = {}
+
+
+def grad_was_sunk(ptr: int) -> bool:
+    return ptr in _sunk
+
+
+def _grad_dst(ptr, shape, device):
+    """(fp32 tensor the kernel writes a parameter gradient to, True if it is the registered sink of the parameter at `ptr`)."""
+    v = _grad_sinks.get(ptr) if ptr else None
+    if v is not None and v.numel() == math.prod(shape) and v.data_ptr() % 16 == 0:
+        _sunk.add(ptr)
+        return v.view(shape), True
+    return torch.empty(shape, dtype=torch.float32, device=device), False
+
+
+def _run_bwd_callback(ptr) -> None:
+    cb = _bwd_callbacks.get(ptr) if _bwd_callbacks else None
+    if cb is not None:
+        cb()
+
+
+def conv3d_wgrad_raw(x0, x1, dy, want_bias=True, side=None, dw_out=None, db_out=None):
     """side: a stream already ordered after the producers of x / dy (see fork_side); the launch then goes there and the
-    call returns (dw, db, workspace) — the caller keeps `workspace` alive until it has joined the side stream."""
+    call returns (dw, db, workspace) — the caller keeps `workspace` alive until it has joined the side stream.
+    dw_out / db_out: destinations (fp32, torch layout) instead of fresh tensors."""
     L = _lib.load()
     N, D, H, W, c0 = x0.shape
     c1 = 0 if x1 is None else x1.shape[-1]
@@ -233,8 +280,8 @@ def conv3d_wgrad_raw(x0, x1, dy, want_bias=True, side=None):
     ws_bytes = L.b200_conv3d_wgrad_workspace(c0, c1, Cout, N, D, H, W)
     # all buffers come from the CURRENT stream's pool, whichever stream the kernels run on
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x0.device)
-    dw = torch.empty((Cout, c0 + c1, 3, 3, 3), dtype=torch.float32, device=x0.device)
-    db = torch.empty(Cout, dtype=torch.float32, device=x0.device) if want_bias else None
+    dw = dw_out if dw_out is not None else torch.empty((Cout, c0 + c1, 3, 3, 3), dtype=torch.float32, device=x0.device)
+    db = (db_out if db_out is not None else torch.empty(Cout, dtype=torch.float32, device=x0.device)) if want_bias else None
     check(
         L.b200_conv3d_wgrad(_dt(x0), _ptr(x0), c0, _ptr(x1), c1, _ptr(dy), Cout, _ptr(dw), _ptr(db), _ptr(ws), ws_bytes,
                             N, D, H, W, _stream() if side is None else side.cuda_stream),
@@ -397,6 +444,8 @@ class _ConvBNAct(torch.autograd.Function):
         ctx.save_for_backward(x0, x1, weight, conv_out, stats, dropmask, prev_conv_out, prev_stats)
         ctx.training = bool(training)
         ctx.has_bias = bias is not None
+        ctx.bias_ptr = bias.data_ptr() if bias is not None else 0
+        ctx.gamma_ptr, ctx.beta_ptr = gamma.data_ptr(), beta.data_ptr()
         ctx.mark_non_differentiable(conv_out, stats)
         ctx.set_materialize_grads(False)      # no zero-filled gradient tensors for the two pass-through outputs
         return y, conv_out, stats
@@ -407,13 +456,14 @@ class _ConvBNAct(torch.autograd.Function):
         x0, x1, weight, conv_out, stats, dropmask, prev_conv_out, prev_stats = ctx.saved_tensors
         if gy is None:                        # (materialize_grads is off) nothing flows back through this block
             return (None,) * 16
+        _run_bwd_callback(weight.data_ptr())
         gy = gy.contiguous()
         N, D, H, W, Cout = conv_out.shape
         M, S = N * D * H * W, D * H * W
         dev = gy.device
         dt = _dt(conv_out)
-        dgamma = torch.empty(Cout, dtype=torch.float32, device=dev)
-        dbeta = torch.empty(Cout, dtype=torch.float32, device=dev)
+        dgamma, g_sunk = _grad_dst(ctx.gamma_ptr, (Cout,), dev)
+        dbeta, b_sunk = _grad_dst(ctx.beta_ptr, (Cout,), dev)
         sums = torch.empty(2 * Cout, dtype=torch.float32, device=dev)
         hit = _bnbwd_handoff.pop(conv_out.data_ptr(), None)
         if hit is not None and hit[2] == gy.data_ptr() and dropmask is None:
@@ -434,7 +484,7 @@ class _ConvBNAct(torch.autograd.Function):
             "bn_act_bwd_apply",
         )
         dx0, dx1, dw, db = _conv_bwd_from_dconv(ctx, x0, x1, weight, dconv, zero_bias_grad=ctx.training, prev=(prev_conv_out, prev_stats))
-        return (dx0, dx1, dw, db, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None)
+        return (dx0, dx1, dw, db, None if g_sunk else dgamma, None if b_sunk else dbeta, None, None, None, None, None, None, None, None, None, None)
 
 
 # (partials, rows, gy.data_ptr()) of a BatchNorm-backward reduction computed by the kernel that produced gy, keyed by the data
@@ -462,14 +512,24 @@ def _conv_bwd_from_dconv(ctx, x0, x1, weight, dconv, zero_bias_grad, prev=(None,
     side = keep = None
     if need_w:
         side = fork_side(dev) if need_x else None
+        dw_dst, w_sunk = _grad_dst(weight.data_ptr(), tuple(weight.shape), dev)
+        bias_ptr = getattr(ctx, "bias_ptr", 0)
+        b_sunk = False
+        db_dst = None
+        if not zero_bias_grad and ctx.has_bias:
+            db_dst, b_sunk = _grad_dst(bias_ptr, (Cout,), dev)
         if side is None:
-            dw, db = conv3d_wgrad_raw(x0, x1, dconv, want_bias=not zero_bias_grad)
+            dw, db = conv3d_wgrad_raw(x0, x1, dconv, want_bias=not zero_bias_grad, dw_out=dw_dst, db_out=db_dst)
         else:
-            dw, db, keep = conv3d_wgrad_raw(x0, x1, dconv, want_bias=not zero_bias_grad, side=side)
-        if db is None:
-            db = torch.zeros(Cout, dtype=torch.float32, device=dev)
-        if not ctx.has_bias:
+            dw, db, keep = conv3d_wgrad_raw(x0, x1, dconv, want_bias=not zero_bias_grad, side=side, dw_out=dw_dst, db_out=db_dst)
+        if w_sunk:
+            dw = None
+        if not ctx.has_bias or b_sunk:
             db = None
+        elif db is None:
+            # the bias feeds a batch-statistics BatchNorm: its gradient is exactly zero.  With a registered sink the flat slice is
+            # simply left at zero (the trainer zeroes it once); otherwise autograd gets a zero tensor, as the reference's does
+            db = None if bias_ptr in _grad_sinks else torch.zeros(Cout, dtype=torch.float32, device=dev)
     dx0 = dx1 = None
     if need_x:
         c0 = x0.shape[-1]
@@ -540,6 +600,7 @@ class _ConvStats(torch.autograd.Function):
                                                 momentum, impl)
         ctx.save_for_backward(x0, x1, weight, prev_conv_out, prev_stats)
         ctx.has_bias = bias is not None
+        ctx.bias_ptr = bias.data_ptr() if bias is not None else 0
         ctx.mark_non_differentiable(stats)
         ctx.set_materialize_grads(False)
         return conv_out, stats
@@ -549,6 +610,7 @@ class _ConvStats(torch.autograd.Function):
         x0, x1, weight, prev_conv_out, prev_stats = ctx.saved_tensors
         if dconv is None:
             return (None,) * 14
+        _run_bwd_callback(weight.data_ptr())
         dx0, dx1, dw, db = _conv_bwd_from_dconv(ctx, x0, x1, weight, dconv.contiguous(), zero_bias_grad=True, prev=(prev_conv_out, prev_stats))
         return (dx0, dx1, dw, db, None, None, None, None, None, None, None, None, None, None)
 
@@ -584,6 +646,7 @@ class _FusedHead(torch.autograd.Function):
         ctx.save_for_backward(conv_out, stats, w32, logits, y, coef)
         ctx.fw_shape = tuple(fw.shape)
         ctx.has_fb = fb is not None
+        ctx.ptrs = (fw.data_ptr(), fb.data_ptr() if fb is not None else 0, gamma.data_ptr(), beta.data_ptr())
         ctx.label_bytes = lb
         ctx.mark_non_differentiable(logits)
         if conf is not None:
@@ -606,19 +669,21 @@ class _FusedHead(torch.autograd.Function):
         gy = torch.empty_like(conv_out)
         wpart = torch.empty(nb * 4 * (Cin + 1), dtype=torch.float32, device=dev)
         bnpart = torch.empty(nb * 2 * Cin, dtype=torch.float32, device=dev)
-        dw = torch.empty((C, Cin), dtype=torch.float32, device=dev)
-        db = torch.empty(C, dtype=torch.float32, device=dev)
+        fw_ptr, fb_ptr, gamma_ptr, beta_ptr = ctx.ptrs
+        dw, w_sunk = _grad_dst(fw_ptr, (C, Cin), dev)
+        db, fb_sunk = _grad_dst(fb_ptr, (C,), dev)
         check(L.b200_head_bwd(_ptr(logits), _ptr(y), ctx.label_bytes, _ptr(coef), _ptr(go), _ptr(conv_out), _ptr(stats[0]), _ptr(stats[1]),
                               _ptr(stats[2]), _ptr(stats[3]), _ptr(w32), N, S, Cin, C, _ptr(gy), _ptr(wpart), _ptr(bnpart), _ptr(dw), _ptr(db),
                               _stream()), "head_bwd")
-        dgamma = torch.empty(Cin, dtype=torch.float32, device=dev)
-        dbeta = torch.empty(Cin, dtype=torch.float32, device=dev)
+        dgamma, g_sunk = _grad_dst(gamma_ptr, (Cin,), dev)
+        dbeta, b_sunk = _grad_dst(beta_ptr, (Cin,), dev)
         sums = torch.empty(2 * Cin, dtype=torch.float32, device=dev)
         check(L.b200_bn_bwd_finalize_ex(_ptr(bnpart), nb, N * S, Cin, _ptr(dgamma), _ptr(dbeta), _ptr(sums), _stream()), "bn_bwd_finalize_ex")
         dconv = torch.empty_like(conv_out)
         check(L.b200_bn_act_bwd_apply(_dt(conv_out), _ptr(gy), _ptr(conv_out), _ptr(dconv), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]),
                                       _ptr(stats[3]), None, 1, _ptr(sums), 1, N, S, Cin, _stream()), "bn_act_bwd_apply")
-        return (dconv, None, dgamma, dbeta, dw.reshape(ctx.fw_shape), (db if ctx.has_fb else None), None, None, None, None, None, None)
+        return (dconv, None, None if g_sunk else dgamma, None if b_sunk else dbeta, None if w_sunk else dw.reshape(ctx.fw_shape),
+                (db if ctx.has_fb and not fb_sunk else None), None, None, None, None, None, None)
 
 
 def conv_batch_stats(x0, x1, conv, bn, impl=0, prev=None):
@@ -731,6 +796,7 @@ class _ConvT2(torch.autograd.Function):
         check(L.b200_convt2_fwd(_dt(x), _ptr(x), _ptr(w32), _ptr(b32), _ptr(y), N, D, H, W, Cin, Cout, _stream()), "convt2_fwd")
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        ctx.bias_ptr = bias.data_ptr() if bias is not None else 0
         return y
 
     @staticmethod
@@ -747,8 +813,8 @@ class _ConvT2(torch.autograd.Function):
             side = fork_side(x.device) if ctx.needs_input_grad[0] else None
             ws_bytes = L.b200_convt2_wgrad_workspace(Cin, Cout, N, D, H, W)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-            dw = torch.empty_like(w32)
-            db = torch.empty(Cout, dtype=torch.float32, device=x.device)
+            dw, w_sunk = _grad_dst(weight.data_ptr(), tuple(w32.shape), x.device)
+            db, b_sunk = _grad_dst(ctx.bias_ptr, (Cout,), x.device)
             check(
                 L.b200_convt2_bwd_weight(_dt(x), _ptr(x), _ptr(gy), _ptr(dw), _ptr(db), _ptr(ws), ws_bytes, N, D, H, W, Cin, Cout,
                                          _stream() if side is None else side.cuda_stream),
@@ -759,6 +825,10 @@ class _ConvT2(torch.autograd.Function):
             check(L.b200_convt2_bwd_data(_dt(x), _ptr(gy), _ptr(w32), _ptr(gx), N, D, H, W, Cin, Cout, _stream()), "convt2_bwd_data")
         join_side(side, x.device, x, gy, ws)
         del ws
+        if need_w and w_sunk:
+            dw = None
+        if need_w and b_sunk:
+            db = None
         return gx, dw, (db if ctx.has_bias else None)
 
 
@@ -814,6 +884,7 @@ class _FinalConv1x1(torch.autograd.Function):
         check(L.b200_conv1x1_fwd(_dt(x), _ptr(x), _ptr(w32), _ptr(b32), _ptr(y), N, S, Cin, Cout, int(round_bf16), _stream()), "conv1x1_fwd")
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        ctx.bias_ptr = bias.data_ptr() if bias is not None else 0
         return y
 
     @staticmethod
@@ -826,15 +897,15 @@ class _FinalConv1x1(torch.autograd.Function):
         S = D * H * W
         w32 = _f32(weight).reshape(Cout, Cin)
         gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        dw = torch.empty((Cout, Cin), dtype=torch.float32, device=x.device)
-        db = torch.empty(Cout, dtype=torch.float32, device=x.device)
+        dw, w_sunk = _grad_dst(weight.data_ptr(), (Cout, Cin), x.device)
+        db, b_sunk = _grad_dst(ctx.bias_ptr, (Cout,), x.device)
         partials = torch.empty(L.b200_conv1x1_partials_bytes(Cin, Cout) // 4, dtype=torch.float32, device=x.device)
         check(
             L.b200_conv1x1_bwd(_dt(x), _ptr(x), _ptr(w32), _ptr(gy), _ptr(gx), _ptr(dw), _ptr(db), _ptr(partials), N, S, Cin, Cout,
                                _stream()),
             "conv1x1_bwd",
         )
-        return gx, dw.reshape(weight.shape), (db if ctx.has_bias else None), None
+        return gx, (None if w_sunk else dw.reshape(weight.shape)), (db if ctx.has_bias and not b_sunk else None), None
 
 
 def final_conv1x1(x, weight, bias, round_bf16=False):

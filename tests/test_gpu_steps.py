@@ -539,3 +539,39 @@ def test_bn_backward_reduction_rides_on_the_data_gradient_kernel(cuda_dev):
     assert rel_l2(a, b) <= 1e-3, rel_l2(a, b)
     for k in ("encoder.0.double_conv.1.weight", "encoder.0.double_conv.1.bias", "decoder.3.double_conv.1.weight", "decoder.3.double_conv.1.bias"):
         assert rel_l2(gf[k], gu[k]) <= 5e-4, (k, rel_l2(gf[k], gu[k]))      # fp32 sums over 1.5 M voxels in two different orders
+
+
+@pytest.mark.gpu
+def test_gradient_sinks_match_gathered_gradients_and_leave_no_aten_kernels(cuda_dev):
+    """SURVEY 8f-1 (train_unet.py:226): the backward kernels write parameter gradients straight into the trainer's flat buffer.
+    Same bits as the gather path (per-parameter tensors + multi-tensor copy + zero fills), parameters still show .grad, and the
+    captured step launches no ATen kernel (no fills, no multi-tensor copies): only this library's kernels."""
+    sd = init_state_dict(1, 4, seed=0)
+    x, y = structured_volume(2, 32, seed=5)
+    xc, yc = x.cuda(), y.cuda()
+    flats, grads = [], []
+    for sinks in (True, False):
+        net = UNet3D(1, 4, dropout_rate=0.0).cuda(); net.load_state_dict(sd); net.train()
+        tr = DataParallelTrainer(net, M.combined_loss, lr=1e-3, autocast_dtype=torch.bfloat16, metrics_fn="confusion")
+        tr._grad_sinks_on = sinks
+        for _ in range(2):
+            tr.step(xc, yc)
+        torch.cuda.synchronize()
+        flats.append(tr.fp.flat.clone()); grads.append(tr.fp.grad.clone())
+        if sinks:
+            for (n, p), v in zip(tr.fp.order, tr.fp._views):
+                assert p.grad is not None and p.grad.data_ptr() == v.data_ptr(), n
+            sunk_trainer = tr
+    assert torch.equal(grads[0], grads[1])
+    assert torch.equal(flats[0], flats[1])
+    # kernel inventory of one captured step
+    tr = sunk_trainer
+    tr.capture(xc, yc, warmup=1)
+    tr.replay(); torch.cuda.synchronize()
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        tr.replay()
+        torch.cuda.synchronize()
+    names = [e.key for e in prof.key_averages() if e.device_type == torch.autograd.DeviceType.CUDA]
+    aten = [n for n in names if n.startswith("at::") or "at::native" in n or "elementwise_kernel" in n or "multi_tensor_apply" in n]
+    assert names and not aten, aten
