@@ -52,6 +52,22 @@ __device__ __forceinline__ uint64_t desc_mn_sw64(uint32_t addr, uint32_t lbo_byt
   return d;
 }
 
+#define B200_WG3_MMA(NAME, QUAL)                                                                                             \
+  __device__ __forceinline__ void NAME(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc) {                                  \
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, 1, 0;\ntcgen05.mma.cta_group::1.kind::f16" QUAL " [%0], %1, %2, %3, p;\n}" \
+                 ::"r"(d), "l"(a), "l"(b), "r"(idesc) : "memory");                                                           \
+  }
+B200_WG3_MMA(mma_fill, ".collector::a::fill")
+B200_WG3_MMA(mma_use, ".collector::a::use")
+B200_WG3_MMA(mma_last, ".collector::a::lastuse")
+
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc3_kernel(const Wg3Params g, const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_q0,
                  const __grid_constant__ CUtensorMap tm_q1) {
@@ -63,7 +79,7 @@ wgrad_tc3_kernel(const Wg3Params g, const __grid_constant__ CUtensorMap tm_p, co
   auto q_empty = [&](int i) { return bar0 + 8u * (3 + i); };
   auto p_full = [&](int i) { return bar0 + 8u * (6 + i); };
   auto p_empty = [&](int i) { return bar0 + 8u * (10 + i); };
-  const uint32_t acc_done = bar0 + 8u * 14;
+  const uint32_t acc_done = bar0 + 8u * 14, acc_zero = bar0 + 8u * 15;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 192);
   uint8_t* pbuf = smem + 1024;                   // stage bases stay 1024-byte aligned (kPBytes, kQBytes are multiples of 512)
   uint8_t* qbuf = pbuf + kPStages * kPBytes;
@@ -81,6 +97,7 @@ wgrad_tc3_kernel(const Wg3Params g, const __grid_constant__ CUtensorMap tm_p, co
     for (int i = 0; i < kQStages; ++i) { tc::mbar_init(q_full(i), 1); tc::mbar_init(q_empty(i), 1); }
     for (int i = 0; i < kPStages; ++i) { tc::mbar_init(p_full(i), 1); tc::mbar_init(p_empty(i), 1); }
     tc::mbar_init(acc_done, 1);
+    tc::mbar_init(acc_zero, 4);
     tc::fence_barrier_init();
   }
   if (warp == 2) {
@@ -131,7 +148,8 @@ wgrad_tc3_kernel(const Wg3Params g, const __grid_constant__ CUtensorMap tm_p, co
       const uint32_t a_hi = (uint32_t)(a_proto >> 32), a_lo0 = (uint32_t)a_proto;
       const uint32_t b_hi = (uint32_t)(b_proto >> 32), b_lo0 = (uint32_t)b_proto;
       constexpr uint32_t kARow16 = kQRowBytes >> 4, kBRow16 = kPRowBytes >> 4;
-      uint32_t touched = 0;  // bit kd: accumulator already holds data
+      tc::mbar_wait(acc_zero, 0);      // the epilogue warps have zeroed the three accumulators: every instruction accumulates
+      tc::tc_fence_after();
       int p_ready = 0;
       for (int qi = 0; qi <= planes + 1; ++qi) {
         const int q = qi - 1;
@@ -144,35 +162,36 @@ wgrad_tc3_kernel(const Wg3Params g, const __grid_constant__ CUtensorMap tm_p, co
         }
         tc::tc_fence_after();
         const uint32_t q_lo = a_lo0 + (tc::smem_u32(qbuf + qst * kQBytes) >> 4);
+        // dY plane q - kd + 1 meets this X plane through kd; kd_lo .. kd_hi are the planes this CTA owns
+        const int kd_lo = max(0, q + 2 - planes), kd_hi = min(2, q + 1);
+        uint32_t p_lo[3];
 #pragma unroll
-        for (int kd = 0; kd < 3; ++kd) {
-          const int pl = q - kd + 1;
-          if (pl < 0 || pl >= planes) continue;
-          const uint32_t p_lo = b_lo0 + (tc::smem_u32(pbuf + (pl % kPStages) * kPBytes) >> 4);
-          const uint32_t d_tmem = tmem_base + (uint32_t)(kd * 3 * kCW);
-          const bool fresh = ((touched >> kd) & 1u) == 0;
-          auto adesc = [&](int rho) { return ((uint64_t)a_hi << 32) | (q_lo + (uint32_t)rho * kARow16); };
-          auto bdesc = [&](int row) { return ((uint64_t)b_hi << 32) | (p_lo + (uint32_t)row * kBRow16); };
-          // halo row rho pairs with tile rows rho-2+j (j = kh' = 2-kh): valid j in [max(0, 2-rho), min(2, 17-rho)]
-          if (fresh) {
-            // the first three halo rows open the three kh' column blocks one by one (accumulate = 0 overwrites)
-            tc::umma_bf16_ss(d_tmem + 2 * kCW, adesc(0), bdesc(0), idesc_n[1], 0);   // rho 0: j = 2 (row 0)
-            tc::umma_bf16_ss(d_tmem + kCW, adesc(1), bdesc(0), idesc_n[1], 0);       // rho 1: j = 1 (row 0, fresh)
-            tc::umma_bf16_ss(d_tmem + 2 * kCW, adesc(1), bdesc(1), idesc_n[1], 1);   //        j = 2 (row 1)
-            tc::umma_bf16_ss(d_tmem, adesc(2), bdesc(0), idesc_n[1], 0);             // rho 2: j = 0 (row 0, fresh)
-            tc::umma_bf16_ss(d_tmem + kCW, adesc(2), bdesc(1), idesc_n[2], 1);       //        j = 1, 2 (rows 1, 2)
-          }
+        for (int kd = 0; kd < 3; ++kd) p_lo[kd] = b_lo0 + (tc::smem_u32(pbuf + ((q - kd + 1 + kPStages) % kPStages) * kPBytes) >> 4);
+        // halo row rho pairs with tile rows rho-2+j (j = kh' = 2-kh): valid j in [max(0, 2-rho), min(2, 17-rho)]
+        if (kd_lo == 0 && kd_hi == 2) {
+          // interior plane: the three kd instructions of a halo row share A through the collector (48 instead of 56 cycles at N = 96)
 #pragma unroll
           for (int rho = 0; rho < 18; ++rho) {
-            if (fresh && rho < 3) continue;
             const int j_lo = rho < 2 ? 2 - rho : 0, j_hi = rho > 15 ? 17 - rho : 2;
-            tc::umma_bf16_ss(d_tmem + j_lo * kCW, adesc(rho), bdesc(rho - 2 + j_lo), idesc_n[j_hi - j_lo + 1], 1);
+            const uint64_t ad = ((uint64_t)a_hi << 32) | (q_lo + (uint32_t)rho * kARow16);
+            const uint32_t boff = (uint32_t)(rho - 2 + j_lo) * kBRow16, col = tmem_base + (uint32_t)(j_lo * kCW);
+            const uint32_t idesc = idesc_n[j_hi - j_lo + 1];
+            mma_fill(col, ad, ((uint64_t)b_hi << 32) | (p_lo[0] + boff), idesc);
+            mma_use(col + 3 * kCW, ad, ((uint64_t)b_hi << 32) | (p_lo[1] + boff), idesc);
+            mma_last(col + 6 * kCW, ad, ((uint64_t)b_hi << 32) | (p_lo[2] + boff), idesc);
           }
-        }
+        } else {
 #pragma unroll
-        for (int kd = 0; kd < 3; ++kd) {
-          const int pl = q - kd + 1;
-          if (pl >= 0 && pl < planes) touched |= 1u << kd;
+          for (int kd = 0; kd < 3; ++kd) {
+            if (kd < kd_lo || kd > kd_hi) continue;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(kd * 3 * kCW);
+#pragma unroll
+            for (int rho = 0; rho < 18; ++rho) {
+              const int j_lo = rho < 2 ? 2 - rho : 0, j_hi = rho > 15 ? 17 - rho : 2;
+              const uint64_t ad = ((uint64_t)a_hi << 32) | (q_lo + (uint32_t)rho * kARow16);
+              tc::umma_bf16_ss(d_tmem + j_lo * kCW, ad, ((uint64_t)b_hi << 32) | (p_lo[kd] + (uint32_t)(rho - 2 + j_lo) * kBRow16), idesc_n[j_hi - j_lo + 1], 1);
+            }
+          }
         }
         tc::umma_commit(q_empty(qst));
         if (q - 1 >= 0 && q - 1 < planes) tc::umma_commit(p_empty((q - 1) % kPStages));
@@ -183,6 +202,12 @@ wgrad_tc3_kernel(const Wg3Params g, const __grid_constant__ CUtensorMap tm_p, co
     // ===================== epilogue: TMEM -> partial dW =====================
     // accumulator row m = kw*32 + ci is TMEM lane m: warp ew holds kw = ew, lane = ci
     const int ew = warp - 4;
+#pragma unroll
+    for (int c = 0; c < 9 * kCW; c += 16) tmem_st16_zero(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c);
+    tmem_st_wait();
+    tc::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(acc_zero);
     tc::mbar_wait(acc_done, 0);
     tc::tc_fence_after();
     const int64_t cta = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
