@@ -33,7 +33,7 @@ rows = []
 for e in last:
     s = e.time_range.start - t0
     d = e.time_range.end - e.time_range.start
-    rows.append((s, d, getattr(e, "stream", getattr(e, "device_resource_id", -1)), e.name.split("(")[0].replace("(anonymous namespace)::", "").replace("void ", "")[:60]))
+    rows.append((s, d, getattr(e, "stream", getattr(e, "device_resource_id", -1)), e.name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0][:60]))
 span = max(s + d for s, d, _, _ in rows)
 # union of busy intervals
 iv = sorted((s, s + d) for s, d, _, _ in rows)
@@ -54,6 +54,12 @@ for st, v in sorted(streams.items(), key=lambda kv: -kv[1]):
     print(f"  stream {st}: kernel time {v:.1f} us")
 print("largest idle gaps (us, at):", [(round(g, 1), round(a, 1)) for g, a in sorted(gaps, reverse=True)[:12]])
 print("gap histogram:", collections.Counter(min(int(g), 10) for g, _ in gaps))
+byname = collections.defaultdict(lambda: [0.0, 0])
+for s, d, st, n in rows:
+    byname[(st, n)][0] += d
+    byname[(st, n)][1] += 1
+for (st, n), (v, c) in sorted(byname.items(), key=lambda kv: -kv[1][0]):
+    print(f"  {v:8.1f} us x{c:3d} s{st} {n}")
 if "--all" in sys.argv:
     for s, d, st, n in rows:
         print(f"{s:9.1f} {d:8.1f} s{st} {n}")
