@@ -25,6 +25,9 @@
 // epilogue folds the (p, p') blocks of a tap (lanes 16 apart: one shuffle) and writes two partial slices per CTA (g' = 0, 1
 // carry the same taps from different halo rows); partials are reduced in fixed order (partial_reduce.cuh, deterministic).
 // Halo and ragged tiles are zero-filled by the TMA unit; planes outside the volume are skipped.
+// Not extensible to 16-channel slabs of wider tensors (16 -> 32, encoder.1.c0): a TMA box whose inner extent (32 B) is narrower
+// than its swizzle span lands in 64-byte slots, half of each unwritten (measured: tools/tma_inner32_probe.cu), so the voxel-pair
+// rows cannot be formed from a 32-channel tensor; that layer stays on wgrad_tc2.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "tma_maps.cuh"
