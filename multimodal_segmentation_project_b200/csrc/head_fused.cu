@@ -216,92 +216,167 @@ head_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ scale, con
 
 // coef layout = seg_loss_finalize's: [0] w_ce / Nvox, [1] kd (unused here), [2 + c] a_c, [2 + C + c] b_c
 // wpart[block][CMAX * (CIN + 1)] = partial dW (co, ci) and db (co, CIN); bnpart[block][2][CIN] = partial (sum g, invstd * sum g * (x - mean))
-template <typename LabelT>
+//
+// Two threads per voxel, eight channels each (lane parity = channel half): 32 dW + 16 BatchNorm accumulators per thread instead of
+// 64 + 32, parameters and weights read from shared memory as float4 and shared by the U voxels of an iteration, every global
+// load and store a full 16 bytes per lane on consecutive addresses.  (First version: one thread per voxel and all 16 channels —
+// 128 registers with 320 bytes of spills, 112 scalar LDS per voxel, 2 x 256 threads per SM: 185-255 us for a 41 us traffic floor.)
+// Both threads of a pair evaluate the softmax (cheaper than exchanging it).  gy is bit-identical to the first version (same fma
+// chains); dW / db / BatchNorm sums are folded in a different, still fixed, order.
+template <typename LabelT, int U>
 __global__ void __launch_bounds__(kThreads, 2)
 head_bwd_kernel(const float* __restrict__ logits, const LabelT* __restrict__ target, const float* __restrict__ coef, const float* __restrict__ gout,
                 const bf16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                 const float* __restrict__ invstd, const float* __restrict__ w, int64_t N, int64_t S, int C, bf16* __restrict__ gy,
                 float* __restrict__ wpart, float* __restrict__ bnpart) {
   constexpr int P = CMAX * (CIN + 1);
-  __shared__ float ws[CMAX * CIN + 3 * CIN];
+  constexpr int HC = CIN / 2;                           // channels per thread
+  __shared__ __align__(16) float ws[CMAX * CIN + 3 * CIN];
   __shared__ float red[kThreads / 32][P + 2 * CIN];
-  float* sc = ws + CMAX * CIN; float* sh = sc + CIN; float* mu = sh + CIN;
   for (int i = threadIdx.x; i < CMAX * CIN; i += blockDim.x) ws[i] = i < C * CIN ? w[i] : 0.f;
-  if (threadIdx.x < CIN) { sc[threadIdx.x] = scale[threadIdx.x]; sh[threadIdx.x] = shift[threadIdx.x]; mu[threadIdx.x] = mean[threadIdx.x]; }
+  if (threadIdx.x < CIN) {
+    ws[CMAX * CIN + threadIdx.x] = scale[threadIdx.x]; ws[CMAX * CIN + CIN + threadIdx.x] = shift[threadIdx.x];
+    ws[CMAX * CIN + 2 * CIN + threadIdx.x] = mean[threadIdx.x];
+  }
   __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = lane & 1, vl = lane >> 1;
+  const float4* w4 = reinterpret_cast<const float4*>(ws) + half * 2;                       // + co * 4 + q
+  const float4* sc4 = reinterpret_cast<const float4*>(ws + CMAX * CIN) + half * 2;
+  const float4* sh4 = sc4 + CIN / 4; const float4* mu4 = sh4 + CIN / 4;
   const float go = gout[0];
   const float w_ce = coef[0] * go;
   float ca[CMAX], cb[CMAX];
 #pragma unroll
   for (int c = 0; c < CMAX; ++c) { ca[c] = c < C ? coef[2 + c] * go : 0.f; cb[c] = c < C ? coef[2 + C + c] * go : 0.f; }
-  float dw[CMAX][CIN], db[CMAX], a0[CIN], a1[CIN];
+  float dw[CMAX][HC], db[CMAX], a0[HC], a1[HC];
 #pragma unroll
   for (int co = 0; co < CMAX; ++co) {
     db[co] = 0.f;
 #pragma unroll
-    for (int k = 0; k < CIN; ++k) dw[co][k] = 0.f;
+    for (int k = 0; k < HC; ++k) dw[co][k] = 0.f;
   }
 #pragma unroll
-  for (int k = 0; k < CIN; ++k) a0[k] = a1[k] = 0.f;
+  for (int k = 0; k < HC; ++k) a0[k] = a1[k] = 0.f;
 
-  const int64_t total = N * S, stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += stride) {
-    const int64_t n = v / S, sp = v - n * S;
-    float z[CMAX];
+  // a warp covers 16 * U consecutive voxels per iteration; every sample is walked separately (no 64-bit division per voxel)
+  const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * (16 * U);
+  for (int64_t n = 0; n < N; ++n) {
+    const bf16* xn = x + n * S * CIN;
+    bf16* gn = gy + n * S * CIN;
+    const LabelT* tn = target + n * S;
+    const float* ln = logits + n * C * S;
+    for (int64_t vb = ((int64_t)blockIdx.x * (kThreads / 32) + warp) * (16 * U); vb < S; vb += wstride) {
+      uint4 raw[U];
+      float z[U][CMAX];
+      int yy[U];
+      bool act[U];
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) z[c] = c < C ? __ldcs(logits + (n * C + c) * S + sp) : 0.f;
-    uint4 raw[2];
-    raw[0] = __ldcs(reinterpret_cast<const uint4*>(x + v * CIN));
-    raw[1] = __ldcs(reinterpret_cast<const uint4*>(x + v * CIN) + 1);
-    const int yy = (int)target[v];
-    Softmax4 sm;
-    sm.compute(z, C);
-    float wv[CMAX], pw = 0.f, dz[CMAX];
+      for (int u = 0; u < U; ++u) {
+        const int64_t v = vb + u * 16 + vl;
+        act[u] = v < S;
+        raw[u] = make_uint4(0, 0, 0, 0);
+        yy[u] = -1;
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c)
-      if (c < C) { wv[c] = (c == yy ? ca[c] : 0.f) + cb[c]; pw += sm.p[c] * wv[c]; }
+        for (int c = 0; c < CMAX; ++c) z[u][c] = 0.f;
+        if (act[u]) {
+          raw[u] = __ldcs(reinterpret_cast<const uint4*>(xn + v * CIN) + half);
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) dz[c] = c < C ? w_ce * (sm.p[c] - (c == yy ? 1.f : 0.f)) + sm.p[c] * (wv[c] - pw) : 0.f;
-    float xc[CIN], y[CIN];
-    bn_relu16(raw, sc, sh, mu, xc, y);
-    uint32_t packed[8];
-    float g[CIN];
+          for (int c = 0; c < CMAX; ++c)
+            if (c < C) z[u][c] = __ldcs(ln + c * S + v);
+          yy[u] = (int)tn[v];
+        }
+      }
+      // the U voxels are finished one after the other (loads above stay in flight): live state per voxel ~ 40 registers
 #pragma unroll
-    for (int k = 0; k < CIN; ++k) {
-      float a = 0.f;
+      for (int u = 0; u < U; ++u) {
+        float dz[CMAX], xc[HC], y[HC];
+        {
+          Softmax4 sm;
+          sm.compute(z[u], C);
+          float wv[CMAX], pw = 0.f;
 #pragma unroll
-      for (int co = 0; co < CMAX; ++co) a = fmaf(dz[co], ws[co * CIN + k], a);
-      const bf16 r = __float2bfloat16_rn(a);                 // gradient w.r.t. the normalised activation, stored as bf16
-      g[k] = y[k] > 0.f ? __bfloat162float(r) : 0.f;         // ... and through the ReLU (y > 0 <=> pre-activation > 0)
-      if (k & 1) packed[k >> 1] |= (uint32_t)__bfloat16_as_ushort(r) << 16; else packed[k >> 1] = (uint32_t)__bfloat16_as_ushort(r);
-      a0[k] += g[k];
-      a1[k] = fmaf(g[k], xc[k], a1[k]);
-    }
-    reinterpret_cast<uint4*>(gy + v * CIN)[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    reinterpret_cast<uint4*>(gy + v * CIN)[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+          for (int c = 0; c < CMAX; ++c)
+            if (c < C) { wv[c] = (c == yy[u] ? ca[c] : 0.f) + cb[c]; pw += sm.p[c] * wv[c]; }
 #pragma unroll
-    for (int co = 0; co < CMAX; ++co) {
-      db[co] += dz[co];
+          for (int c = 0; c < CMAX; ++c)
+            dz[c] = (c < C && act[u]) ? w_ce * (sm.p[c] - (c == yy[u] ? 1.f : 0.f)) + sm.p[c] * (wv[c] - pw) : 0.f;
+        }
+        // BatchNorm + ReLU of this thread's eight channels (the forward kernels' arithmetic: fma in fp32, rounded to bf16, max with 0)
 #pragma unroll
-      for (int k = 0; k < CIN; ++k) dw[co][k] = fmaf(dz[co], y[k], dw[co][k]);
+        for (int q = 0; q < 2; ++q) {
+          const float4 sc = sc4[q], sh = sh4[q], mu = mu4[q];
+          const uint32_t w0 = q == 0 ? raw[u].x : raw[u].z, w1 = q == 0 ? raw[u].y : raw[u].w;
+          xc[4 * q] = __uint_as_float(w0 << 16) - mu.x;
+          xc[4 * q + 1] = __uint_as_float(w0 & 0xffff0000u) - mu.y;
+          xc[4 * q + 2] = __uint_as_float(w1 << 16) - mu.z;
+          xc[4 * q + 3] = __uint_as_float(w1 & 0xffff0000u) - mu.w;
+          const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+          const __nv_bfloat162 p01 = __hmax2(__floats2bfloat162_rn(fmaf(xc[4 * q], sc.x, sh.x), fmaf(xc[4 * q + 1], sc.y, sh.y)), zero);
+          const __nv_bfloat162 p23 = __hmax2(__floats2bfloat162_rn(fmaf(xc[4 * q + 2], sc.z, sh.z), fmaf(xc[4 * q + 3], sc.w, sh.w)), zero);
+          const uint32_t b01 = *reinterpret_cast<const uint32_t*>(&p01), b23 = *reinterpret_cast<const uint32_t*>(&p23);
+          y[4 * q] = __uint_as_float(b01 << 16);
+          y[4 * q + 1] = __uint_as_float(b01 & 0xffff0000u);
+          y[4 * q + 2] = __uint_as_float(b23 << 16);
+          y[4 * q + 3] = __uint_as_float(b23 & 0xffff0000u);
+        }
+        // gradient w.r.t. the normalised activation: a[k] = sum_co dz[co] * W[co][k] (classes in ascending order from 0)
+        float a[HC];
+#pragma unroll
+        for (int k = 0; k < HC; ++k) a[k] = 0.f;
+#pragma unroll
+        for (int co = 0; co < CMAX; ++co)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const float4 wv = w4[co * 4 + q];
+            a[4 * q] = fmaf(dz[co], wv.x, a[4 * q]);
+            a[4 * q + 1] = fmaf(dz[co], wv.y, a[4 * q + 1]);
+            a[4 * q + 2] = fmaf(dz[co], wv.z, a[4 * q + 2]);
+            a[4 * q + 3] = fmaf(dz[co], wv.w, a[4 * q + 3]);
+          }
+        uint32_t packed[HC / 2];
+#pragma unroll
+        for (int k = 0; k < HC; k += 2) {
+          const __nv_bfloat162 r = __floats2bfloat162_rn(a[k], a[k + 1]);      // stored as bf16 ...
+          const uint32_t rb = *reinterpret_cast<const uint32_t*>(&r);
+          packed[k >> 1] = rb;
+          // ... and through the ReLU (y > 0 <=> pre-activation > 0)
+          const float g0 = y[k] > 0.f ? __uint_as_float(rb << 16) : 0.f, g1 = y[k + 1] > 0.f ? __uint_as_float(rb & 0xffff0000u) : 0.f;
+          a0[k] += g0;
+          a0[k + 1] += g1;
+          a1[k] = fmaf(g0, xc[k], a1[k]);
+          a1[k + 1] = fmaf(g1, xc[k + 1], a1[k + 1]);
+        }
+        if (act[u]) __stcs(reinterpret_cast<uint4*>(gn + (vb + u * 16 + vl) * CIN) + half, make_uint4(packed[0], packed[1], packed[2], packed[3]));
+#pragma unroll
+        for (int co = 0; co < CMAX; ++co) {
+          if (half == 0) db[co] += dz[co];
+#pragma unroll
+          for (int k = 0; k < HC; ++k) dw[co][k] = fmaf(dz[co], y[k], dw[co][k]);
+        }
+      }
     }
   }
-  // fixed-shape fold: warp butterflies, then the warps in order
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // fixed-shape fold: butterflies over the 16 lanes of one parity, then the warps in order
+  auto half_sum = [](float v) {
+#pragma unroll
+    for (int o = 2; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
 #pragma unroll
   for (int co = 0; co < CMAX; ++co) {
 #pragma unroll
-    for (int k = 0; k < CIN; ++k) {
-      const float t = warp_sum(dw[co][k]);
-      if (lane == 0) red[warp][co * (CIN + 1) + k] = t;
+    for (int k = 0; k < HC; ++k) {
+      const float t = half_sum(dw[co][k]);
+      if (lane < 2) red[warp][co * (CIN + 1) + half * HC + k] = t;
     }
-    const float t = warp_sum(db[co]);
+    const float t = half_sum(db[co]);
     if (lane == 0) red[warp][co * (CIN + 1) + CIN] = t;
   }
 #pragma unroll
-  for (int k = 0; k < CIN; ++k) {
-    const float t0 = warp_sum(a0[k]), t1 = warp_sum(a1[k]);
-    if (lane == 0) { red[warp][P + k] = t0; red[warp][P + CIN + k] = t1; }
+  for (int k = 0; k < HC; ++k) {
+    const float t0 = half_sum(a0[k]), t1 = half_sum(a1[k]);
+    if (lane < 2) { red[warp][P + half * HC + k] = t0; red[warp][P + CIN + half * HC + k] = t1; }
   }
   __syncthreads();
   for (int q = threadIdx.x; q < P + 2 * CIN; q += blockDim.x) {
@@ -363,10 +438,10 @@ extern "C" int b200_head_bwd(const float* logits, const void* target, int label_
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = b200_head_blocks(N, S);
   if (label_bytes == 1)
-    head_bwd_kernel<uint8_t><<<grid, kThreads, 0, st>>>(logits, (const uint8_t*)target, coef, gout, (const bf16*)x, scale, shift, mean, invstd, w, N, S, C,
+    head_bwd_kernel<uint8_t, 2><<<grid, kThreads, 0, st>>>(logits, (const uint8_t*)target, coef, gout, (const bf16*)x, scale, shift, mean, invstd, w, N, S, C,
                                                         (bf16*)gy, wpart, bnpart);
   else
-    head_bwd_kernel<int64_t><<<grid, kThreads, 0, st>>>(logits, (const int64_t*)target, coef, gout, (const bf16*)x, scale, shift, mean, invstd, w, N, S, C,
+    head_bwd_kernel<int64_t, 2><<<grid, kThreads, 0, st>>>(logits, (const int64_t*)target, coef, gout, (const bf16*)x, scale, shift, mean, invstd, w, N, S, C,
                                                         (bf16*)gy, wpart, bnpart);
   B200_CHECK_LAUNCH("head_bwd");
   head_bwd_finalize_kernel<<<1, 128, 0, st>>>(wpart, grid, C, dw, db);
