@@ -239,14 +239,23 @@ def test_cfg4_dann_step_128_bf16(cuda_dev):
     (task_c + lam * dom_c).backward()
     keys = [k for k in trainable(sd) if not _skip_bias(k)]
     ours, ref_g = _grads(dict(seg.named_parameters()), {k: p[k].grad for k in keys}, keys)
-    dg = rel_l2(torch.cat([q.grad.flatten() for _, q in disc.named_parameters()]), torch.cat([d_[k].grad.flatten() for k, _ in disc.named_parameters()]))
+    ours_d = torch.cat([q.grad.flatten() for _, q in disc.named_parameters()])
+    dg_e2e = rel_l2(ours_d, torch.cat([d_[k].grad.flatten() for k, _ in disc.named_parameters()]))
+    # The discriminator sees FOUR feature rows: one hidden ReLU whose pre-activation sits within the bf16 distance of the two feature
+    # computations (1.6e-3 here) of zero flips a whole row of dW1, so the end-to-end discriminator gradient is a step function of the
+    # features (measured 0.006 and 0.077 on two sets of warm weights 1e-3 apart).  The head itself is therefore pinned on OUR features
+    # (fp32 kernels against the fp32 oracle), the feature path by `features`, and the gradient that flows back through the
+    # reversal by `seg_grads`; the end-to-end number is recorded with a bound that only catches a broken head.
+    d2 = {k: v.clone().cuda().requires_grad_(True) for k, v in dsd.items()}
+    (lam * OD.domain_loss(d2, f_s.detach().float(), f_t.detach().float(), lam)).backward()
+    dg = rel_l2(ours_d, torch.cat([d2[k].grad.flatten() for k, _ in disc.named_parameters()]))
     rec = dict(test="cfg4_dann_128_bf16", source_logits=rel_l2(o_s, so), features=rel_l2(f_s, sf), task=task_c.item(), task_oracle=task.item(),
-               domain=dom_c.item(), domain_oracle=dom.item(), seg_grads=rel_l2(ours, ref_g), disc_grads=dg)
+               domain=dom_c.item(), domain_oracle=dom.item(), seg_grads=rel_l2(ours, ref_g), disc_grads=dg, disc_grads_end_to_end=dg_e2e)
     _log(**rec)
     assert rec["source_logits"] <= BF16_TOL and rec["features"] <= BF16_TOL, rec
     assert abs(task_c.item() - task.item()) <= BF16_TOL * abs(task.item()), rec
     assert abs(dom_c.item() - dom.item()) <= BF16_TOL * abs(dom.item()), rec
-    assert rec["seg_grads"] <= BF16_TOL and rec["disc_grads"] <= BF16_TOL, rec
+    assert rec["seg_grads"] <= BF16_TOL and rec["disc_grads"] <= 1e-4 and rec["disc_grads_end_to_end"] <= 0.25, rec
     assert int(seg.state_dict()["decoder.3.double_conv.5.num_batches_tracked"]) == nbt0 + 2   # two forwards per step (App. C-8)
 
 
