@@ -259,11 +259,11 @@ WgPlan make_plan(int c0, int c1, int Cout, int N, int D, int H, int W) {
 // ConvTranspose3d(k=2,s=2) weight gradient on the tensor cores (models/unet.py:56-58):
 //     dW[ci][co][child] = sum_v x[v][ci] * gy[child(v)][co],   child = (dz,dy,dx) of the 2x finer grid
 // Same MN-major / SWIZZLE_32B machinery as above: M = 64 input channels of x (TMA boxes), K = 16 coarse
-// voxels of one tile row, N = 8 children x 16 output channels = 128: producer warps gather the eight
-// child planes of gy into [child][voxel][16 ch] so that the children are the B descriptor's
+// voxels of one tile row, N = 8 children x 16 output channels = 128: the eight child planes of gy arrive
+// as [child][voxel][16 ch] (element-stride-2 TMA boxes) so that the children are the B descriptor's
 // leading-dimension stride.  One 64 x 128 fp32 accumulator in TMEM per CTA, partials reduced in fixed order.
 // =====================================================================================================
-constexpr int kCtThreads = 320;          // 4 gather warps, 4 epilogue warps, MMA warp, TMA warp
+constexpr int kCtThreads = 320;          // w4-7: epilogue, w8: MMA, w9: TMA (w0-3 idle: the epilogue warps must be 4..7 for their TMEM lanes)
 constexpr int kCtStages = 2;
 constexpr int kCtQBytes = 8 * kPSlabBytes;  // 8 child planes of 16x16 voxels x 16 ch
 
@@ -277,7 +277,7 @@ struct CtParams {
 };
 
 __global__ void __launch_bounds__(kCtThreads, 1)
-convt_wgrad_tc_kernel(const CtParams g, const __grid_constant__ CUtensorMap tm_x) {
+convt_wgrad_tc_kernel(const CtParams g, const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_gy) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -302,7 +302,7 @@ convt_wgrad_tc_kernel(const CtParams g, const __grid_constant__ CUtensorMap tm_x
 
   if (warp == 8 && lane == 0) {
     for (int i = 0; i < kCtStages; ++i) {
-      tc::mbar_init(q_full(i), 4); tc::mbar_init(q_empty(i), 1);
+      tc::mbar_init(q_full(i), 1); tc::mbar_init(q_empty(i), 1);
       tc::mbar_init(p_full(i), 1); tc::mbar_init(p_empty(i), 1);
     }
     tc::mbar_init(acc_done, 1);
@@ -317,51 +317,28 @@ convt_wgrad_tc_kernel(const CtParams g, const __grid_constant__ CUtensorMap tm_x
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // ---- gather the 8 child planes of gy for coarse plane d0+i: [child][voxel][16 ch], SWIZZLE_32B
-    const int tid = threadIdx.x;
-    const int FH = 2 * g.H, FW = 2 * g.W, FD = 2 * g.D;
-    const int qoff = qslab * 16;
-    for (int i = 0; i < planes; ++i) {
-      const int st = i % kCtStages;
-      tc::mbar_wait(q_empty(st), ((i / kCtStages) & 1) ^ 1);
-      uint8_t* dst = qbuf + st * kCtQBytes;
-      const int d = d0 + i;
-      for (int base = 0; base < 8 * 256 * 2; base += 128 * 8) {
-        uint4 v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          // item -> (child, coarse voxel, 16-byte piece); consecutive lanes walk the fine row: (w, dx, piece)
-          const int id = base + tid + 128 * j;
-          const int pc = id & 1, dx = (id >> 1) & 1, wv = (id >> 2) & 15, dy = (id >> 6) & 1, hv = (id >> 7) & 15, dz = id >> 11;
-          const int fh = 2 * (h0 + hv) + dy, fw = 2 * (w0 + wv) + dx, fd = 2 * d + dz;
-          v[j] = make_uint4(0, 0, 0, 0);
-          if (h0 + hv < g.H && w0 + wv < g.W && fd < FD) {
-            const int64_t row = (((int64_t)n * FD + fd) * FH + fh) * FW + fw;
-            v[j] = __ldg(reinterpret_cast<const uint4*>(g.gy + row * g.cout + qoff + pc * 8));
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int id = base + tid + 128 * j;
-          const int pc = id & 1, dx = (id >> 1) & 1, wv = (id >> 2) & 15, dy = (id >> 6) & 1, hv = (id >> 7) & 15, dz = id >> 11;
-          const int child = dz * 4 + dy * 2 + dx;
-          *reinterpret_cast<uint4*>(dst + child * kPSlabBytes + swz32((uint32_t)(hv * 16 + wv) * 32 + pc * 16)) = v[j];
-        }
-      }
-      tc::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(q_full(st));
-    }
-  } else if (warp == 9) {
+  if (warp == 9) {
+    // ---- one thread feeds both operands by TMA: the x tile, and the eight child planes of gy through an element-stride-2
+    // tensor map (every other fine voxel in h and w: box = 16 x 16 coarse positions), landing as [child][voxel][16 ch]
+    // SWIZZLE_32B slabs.  (First version: four warps gathered gy with 16-byte __ldg into the swizzled layout — 16 KB in
+    // flight per SM, 148 us for the 134 MB top-level tensor; the TMA version keeps two 64 KB stages in flight.)
     if (lane == 0) {
       tma::prefetch(&tm_x);
+      tma::prefetch(&tm_gy);
       for (int i = 0; i < planes; ++i) {
         const int st = i % kCtStages;
-        tc::mbar_wait(p_empty(st), ((i / kCtStages) & 1) ^ 1);
+        const uint32_t ph = ((i / kCtStages) & 1) ^ 1;
+        tc::mbar_wait(q_empty(st), ph);
+        tc::mbar_arrive_expect_tx(q_full(st), kCtQBytes);
+        const int d = d0 + i;
+#pragma unroll
+        for (int child = 0; child < 8; ++child)
+          tma::load_5d(tc::smem_u32(qbuf + st * kCtQBytes + child * kPSlabBytes), &tm_gy, qslab * 16, 2 * w0 + (child & 1), 2 * h0 + ((child >> 1) & 1),
+                       2 * d + (child >> 2), n, q_full(st));
+        tc::mbar_wait(p_empty(st), ph);
         tc::mbar_arrive_expect_tx(p_full(st), p_stage_bytes);
         for (int ms = 0; ms < g.mslabs; ++ms)
-          tma::load_5d(tc::smem_u32(pbuf + st * p_stage_bytes + ms * kPSlabBytes), &tm_x, mchunk * 64 + ms * 16, w0, h0, d0 + i, n, p_full(st));
+          tma::load_5d(tc::smem_u32(pbuf + st * p_stage_bytes + ms * kPSlabBytes), &tm_x, mchunk * 64 + ms * 16, w0, h0, d, n, p_full(st));
       }
     }
   } else if (warp == 8) {
@@ -435,9 +412,17 @@ CtPlan make_ct_plan(int Cin, int Cout, int N, int D, int H, int W) {
   pl.tiles_w = (W + 15) / 16;
   pl.tiles_h = (H + 15) / 16;
   const int64_t base = (int64_t)pl.tiles_w * pl.tiles_h * N * pl.mchunks * pl.qslabs;
-  int dseg = 8;
-  while (dseg > 1 && base * ((D + dseg - 1) / dseg) < 2 * B200_NUM_SMS) dseg >>= 1;
-  if (dseg > D) dseg = D;
+  // one CTA per SM (two 64-96 KB stages): the d-run minimising CTAs-per-SM x (planes streamed + fixed cost of a CTA: pipeline
+  // fill, 128-column epilogue); longer runs win ties (fewer partials to fold).  (First version: runs of at most 8 planes ->
+  // 256 CTAs = 1.73 waves at the top level.)
+  int dseg = 1;
+  int64_t best = -1;
+  for (int cand = 1; cand <= D && cand <= 64; ++cand) {
+    const int64_t ctas = base * ((D + cand - 1) / cand);
+    const int64_t per_sm = (ctas + B200_NUM_SMS - 1) / B200_NUM_SMS;
+    const int64_t cost = per_sm * (cand + 2);
+    if (best < 0 || cost <= best) { best = cost; dseg = cand; }
+  }
   pl.dseg = dseg;
   pl.dblocks = (D + dseg - 1) / dseg;
   pl.spatial = pl.tiles_w * pl.tiles_h * N * pl.dblocks;
@@ -464,8 +449,10 @@ int b200_convt2_wgrad_tc(const void* x, const void* gy, float* dw, void* workspa
   g.partial = (float*)workspace; g.mrows = pl.mrows; g.mslabs = pl.mslabs;
   g.N = N; g.D = D; g.H = H; g.W = W;
   g.dseg = pl.dseg; g.dblocks = pl.dblocks; g.tiles_w = pl.tiles_w; g.tiles_h = pl.tiles_h;
-  CUtensorMap tm_x;
+  CUtensorMap tm_x, tm_gy;
   int rc = tma::make_ndhwc_map(&tm_x, x, Cin, N, D, H, W, 16, 16);
+  if (rc) return rc;
+  rc = tma::make_ndhwc_map_stride2(&tm_gy, gy, Cout, N, 2 * D, 2 * H, 2 * W, 16, 16);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
@@ -473,7 +460,7 @@ int b200_convt2_wgrad_tc(const void* x, const void* gy, float* dw, void* workspa
     attr_set = true;
   }
   dim3 grid((unsigned)pl.spatial, (unsigned)pl.mchunks, (unsigned)pl.qslabs);
-  convt_wgrad_tc_kernel<<<grid, kCtThreads, pl.smem, stream>>>(g, tm_x);
+  convt_wgrad_tc_kernel<<<grid, kCtThreads, pl.smem, stream>>>(g, tm_x, tm_gy);
   B200_CHECK_LAUNCH("convt2_wgrad_tc");
   launch_partial_reduce((const float*)workspace, pl.spatial, (int64_t)pl.mrows * 128, pl.qslabs * pl.mchunks, CtMap{pl.mchunks, Cin, Cout}, dw, stream);
   B200_CHECK_LAUNCH("convt2_wgrad_tc_reduce");
