@@ -236,6 +236,36 @@ def time_step_kernels(dev, peaks):
     loss = F.seg_loss(lg, tgt, _lib.LOSS_DICE_CE)
     hbm_row("seg_loss_bwd_kernel", _event_time(lambda: torch.autograd.grad(loss, lg, retain_graph=True), flush), vox * (8 * CLASSES + 8))
     hbm_row("confusion_kernel", _event_time(lambda: F.confusion_counts(logits, tgt), flush), vox * (4 * CLASSES + 8))
+    # the single-pass head the step actually runs (uint8 labels): forward = 32 B activation + 1 B label read, 16 B logits written per
+    # voxel; backward = logits + label + activation read, 32 B gradient written
+    t8 = tgt.to(torch.uint8)
+    hsums = torch.empty(4 + 4 * CLASSES, dtype=torch.float64, device=dev)
+    hconf = torch.empty(CLASSES, CLASSES, dtype=torch.int64, device=dev)
+    w2 = wf.reshape(CLASSES, C).contiguous()
+    hbm_row("head_fwd_kernel (BN+ReLU, 1x1 conv, Dice/CE sums, confusion)", _event_time(lambda: L.b200_head_fwd(
+        P(a16), P(stats[0]), P(stats[1]), P(stats[2]), P(w2), P(bf_), 1, P(t8), 1, N, S ** 3, C, CLASSES, P(logits), P(hsums), P(hconf), st()), flush),
+        vox * (2 * C + 1 + 4 * CLASSES))
+    coef = torch.tensor([1.0 / vox, 0.0] + [-1e-7] * CLASSES + [1e-8] * CLASSES, device=dev)
+    go = torch.ones(1, device=dev)
+    nb = L.b200_head_blocks(N, S ** 3)
+    wpart, bnpart = torch.empty(nb * 4 * (C + 1), device=dev), torch.empty(nb * 2 * C, device=dev)
+    hdw, hdb = torch.empty(CLASSES, C, device=dev), torch.empty(CLASSES, device=dev)
+    hbm_row("head_bwd_kernel (dlogits, 1x1 dgrad/wgrad, BN-backward sums)", _event_time(lambda: L.b200_head_bwd(
+        P(logits), P(t8), 1, P(coef), P(go), P(a16), P(stats[0]), P(stats[1]), P(stats[2]), P(stats[3]), P(w2), N, S ** 3, C, CLASSES, P(o16), P(wpart),
+        P(bnpart), P(hdw), P(hdb), st()), flush), vox * (4 * CLASSES + 1 + 2 * C + 2 * C))
+    # up-convolution of the top level (ConvTranspose3d 32 -> 16, 64^3 -> 128^3): coarse tensor + fine tensor once each
+    xc = torch.randn(N, S // 2, S // 2, S // 2, 32, device=dev).bfloat16()
+    wt, bt = torch.randn(32, 16, 2, 2, 2, device=dev) * 0.1, torch.zeros(16, device=dev)
+    ct_bytes = xc.numel() * 2 + a16.numel() * 2
+    gxc = torch.empty_like(xc)
+    Sc = S // 2
+    hbm_row("convt_tc_kernel fwd 32->16 (+ weight pack)", _event_time(lambda: L.b200_convt2_fwd(1, P(xc), P(wt), P(bt), P(o16), N, Sc, Sc, Sc, 32, 16, st()), flush), ct_bytes)
+    hbm_row("convt_tc_kernel dgrad (+ weight pack)", _event_time(lambda: L.b200_convt2_bwd_data(1, P(a16), P(wt), P(gxc), N, Sc, Sc, Sc, 32, 16, st()), flush), ct_bytes)
+    ws_bytes = L.b200_convt2_wgrad_workspace(32, 16, N, Sc, Sc, Sc)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    dwt = torch.empty_like(wt)
+    hbm_row("convt_wgrad_tc_kernel + partial_reduce (bias gradient = channel_sum passed as NULL)", _event_time(lambda: L.b200_convt2_bwd_weight(
+        1, P(xc), P(a16), P(dwt), None, P(ws), ws_bytes, N, Sc, Sc, Sc, 32, 16, st()), flush), ct_bytes)
     return out
 
 
