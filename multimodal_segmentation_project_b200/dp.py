@@ -32,9 +32,11 @@ class FlatParams:
     tail of the forward pass (final conv, decoder, up-convs, bottleneck: 83 % of the U-Net's parameters), then groups of encoder
     levels from the deepest up.  Bucket i is final when backward reaches the first layer of the next group: that layer's
     second-conv weight is the bucket's SENTINEL (a post-accumulate-grad hook on it starts the bucket's all-reduce on a side
-    stream).  Only the last, small bucket (the two top encoder levels: 0.2 MB for the default U-Net) is reduced after backward."""
+    stream).  Only the last, small bucket (the top encoder level: 30 KB for the default U-Net) is reduced after backward, and
+    the trainer hides even that under the optimiser step of the other buckets.  Buckets start on 16-byte boundaries."""
 
-    def __init__(self, module: torch.nn.Module, early_prefixes=("final_conv", "decoder", "upconvs", "bottleneck"), late_levels_per_bucket=2):
+    def __init__(self, module: torch.nn.Module, early_prefixes=("final_conv", "decoder", "upconvs", "bottleneck"), late_levels_per_bucket=3,
+                 tail_levels=1):
         params = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
         early = [(n, p) for n, p in params if n.startswith(tuple(early_prefixes))]
         rest = [(n, p) for n, p in params if not n.startswith(tuple(early_prefixes))]
@@ -42,8 +44,14 @@ class FlatParams:
         groups = [early] if early else []
         # encoder levels, deepest first, `late_levels_per_bucket` levels per bucket; anything else trainable goes last
         covered = set()
-        for i in range(0, len(enc_ids), max(1, late_levels_per_bucket)):
-            ids = enc_ids[i:i + max(1, late_levels_per_bucket)]
+        # the LAST bucket is the only one whose all-reduce cannot hide under backward: it holds just the top `tail_levels` encoder
+        # level(s) (30 KB for the default U-Net), and the trainer hides it under the optimiser step of the other buckets
+        tail = max(0, min(int(tail_levels), len(enc_ids) - 1)) if len(enc_ids) > 1 else 0
+        body_ids = enc_ids[:len(enc_ids) - tail] if tail else enc_ids
+        chunks = [body_ids[i:i + max(1, late_levels_per_bucket)] for i in range(0, len(body_ids), max(1, late_levels_per_bucket))]
+        if tail:
+            chunks.append(enc_ids[len(enc_ids) - tail:])
+        for ids in chunks:
             grp = [(n, p) for n, p in rest if any(n.startswith(f"encoder.{j}.") for j in ids)]
             covered |= {n for n, _ in grp}
             if grp:
@@ -58,27 +66,30 @@ class FlatParams:
             raise ValueError("FlatParams: the module has no trainable parameters")
         self.groups = groups
         self.order = [np_ for g in groups for np_ in g]
-        total = sum(p.numel() for _, p in self.order)
-        # pad so that the fused optimiser can use 128-bit accesses
-        self.total = (total + 3) // 4 * 4
+        # every bucket starts on a 16-byte boundary (the fused optimiser steps bucket ranges with 128-bit accesses); the padding
+        # elements are zeros with zero gradients, which AdamW leaves at zero
+        starts, off = [], 0
+        for g in groups:
+            off = (off + 3) // 4 * 4
+            starts.append(off)
+            off += sum(p.numel() for _, p in g)
+        self.total = (off + 3) // 4 * 4
         dev = self.order[0][1].device
         self.flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(self.total, dtype=torch.float32, device=dev)
-        off = 0
         self.offsets = {}
-        for n, p in self.order:
-            k = p.numel()
-            self.flat[off:off + k].copy_(p.data.reshape(-1))
-            p.data = self.flat[off:off + k].view_as(p)
-            p.grad = self.grad[off:off + k].view_as(p)
-            self.offsets[n] = (off, k)
-            off += k
-        # element / parameter-count boundaries of the buckets
-        self.bucket_elems, self.bucket_params = [0], [0]
+        for g, off in zip(groups, starts):
+            for n, p in g:
+                k = p.numel()
+                self.flat[off:off + k].copy_(p.data.reshape(-1))
+                p.data = self.flat[off:off + k].view_as(p)
+                p.grad = self.grad[off:off + k].view_as(p)
+                self.offsets[n] = (off, k)
+                off += k
+        # element / parameter-count boundaries of the buckets (a bucket's trailing padding rides with it)
+        self.bucket_elems, self.bucket_params = starts + [self.total], [0]
         for g in groups:
-            self.bucket_elems.append(self.bucket_elems[-1] + sum(p.numel() for _, p in g))
             self.bucket_params.append(self.bucket_params[-1] + len(g))
-        self.bucket_elems[-1] = self.total       # the padding rides with the last bucket
         # Sentinel of bucket i (i < last) = a parameter of the autograd node that runs right AFTER the bucket is complete: the second
         # conv of the deepest encoder level of the NEXT group.  AccumulateGrad nodes run with top priority, so when it fires every
         # gradient of the earlier buckets is final.
@@ -197,7 +208,10 @@ class DataParallelTrainer:
             self.opt = FlatAdamW(self.fp.flat, self.fp.grad, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
                                  named_params=named, offsets=self.fp.offsets)
         self.overlap = overlap and self.world > 1 and dev.type == "cuda" and len(self.fp.sentinels) > 0
-        self._side = torch.cuda.Stream(device=dev) if self.overlap else None
+        # the communication stream outranks the main chain (priority -1, see capture()): an all-reduce kernel needs a handful of CTAs
+        # and sits on the step's critical path once backward is over — at default priority the tail all-reduce waited for every
+        # block of the optimiser kernel to be dispatched first (timeline: profiles/r02_timeline_2gpu_graph_replay.txt)
+        self._side = torch.cuda.Stream(device=dev, priority=int(os.environ.get("B200_COMM_STREAM_PRIORITY", "-2"))) if self.overlap else None
         # weight gradients run on a side stream and are joined at the end of backward / before a bucket is gathered:
         # safe here because step() detaches the gradients first (autograd stores, never accumulates)
         self._defer_wgrad = dev.type == "cuda" and os.environ.get("B200_DEFER_WGRAD_JOIN", "1") != "0"
@@ -242,7 +256,14 @@ class DataParallelTrainer:
         # the side stream while the rest of the backward pass continues
         if self.accum > 1 or i != self._buckets_done:
             return  # accumulating: buckets are reduced once, after the last micro-step
-        self._join_wgrads()
+        lo, hi = self.fp.bucket_params[i], self.fp.bucket_params[i + 1]
+        if self._defer_wgrad and all(p.grad is None for _, p in self.fp.order[lo:hi]):
+            # every gradient of the bucket was written into the flat buffer by its kernel (gradient sinks): nothing to copy, so only
+            # the COMMUNICATION stream has to wait for the side-stream weight gradients — the main chain keeps running under them
+            from . import functional as F
+            F.order_after_pending(self._side)
+        else:
+            self._join_wgrads()
         self.fp.gather_bucket(i)
         cur = torch.cuda.current_stream()
         self._side.wait_stream(cur)
@@ -255,17 +276,33 @@ class DataParallelTrainer:
             from . import functional as F
             F.join_pending()
 
-    def allreduce_grads(self):
+    def allreduce_grads(self, defer_last=False):
+        """Reduces the buckets that backward has not launched yet.  defer_last: when only the LAST bucket is left, start its
+        all-reduce on the side stream and return True WITHOUT waiting for it — the current stream has then waited for the earlier
+        buckets only, and the caller must wait for the side stream before it touches the last bucket (see _step_body)."""
         self._join_wgrads()
+        n = self.fp.n_buckets
         done = self._buckets_done if self.overlap else 0
-        for i in range(done, self.fp.n_buckets):
+        for i in range(done, n):
             self.fp.gather_bucket(i)
+        deferred = False
         if self.world > 1:
-            for i in range(done, self.fp.n_buckets):
-                dist.all_reduce(self.fp.bucket(i), op=dist.ReduceOp.SUM, group=self.pg)
-            if done:
-                torch.cuda.current_stream().wait_stream(self._side)
+            if defer_last and self.overlap and n >= 2 and done == n - 1:
+                cur = torch.cuda.current_stream()
+                ev = torch.cuda.Event()
+                ev.record(self._side)                 # the earlier buckets' all-reduces
+                self._side.wait_stream(cur)           # the last weight gradients
+                with torch.cuda.stream(self._side):
+                    dist.all_reduce(self.fp.bucket(n - 1), op=dist.ReduceOp.SUM, group=self.pg)
+                cur.wait_event(ev)
+                deferred = True
+            else:
+                for i in range(done, n):
+                    dist.all_reduce(self.fp.bucket(i), op=dist.ReduceOp.SUM, group=self.pg)
+                if done:
+                    torch.cuda.current_stream().wait_stream(self._side)
         self._buckets_done = 0
+        return deferred
 
     # -- one training step -------------------------------------------------------------------------
     def _step_impl(self, x, y):
@@ -311,12 +348,25 @@ class DataParallelTrainer:
                 if self._one is None or self._one.device != loss.device or self._one.dtype != loss.dtype:
                     self._one = torch.ones_like(loss)
                 loss.backward(gradient=self._one)
-                self.allreduce_grads()
+                split = hasattr(self.opt, "apply_range") and hasattr(self.opt, "begin_step")
+                deferred = self.allreduce_grads(defer_last=split)
             finally:
                 if use_sinks:
                     F.end_grad_sinks()
-            self.opt.step(grad_scale=1.0 / self.world)
-            self._repack()
+            if deferred:
+                # the last bucket (top encoder level) is still being reduced on the side stream: step and repack everything else
+                # under it, then the few kilobytes that were waiting — the tail all-reduce is off the critical path
+                lo = self.fp.bucket_elems[-2]
+                rng = (self.fp.flat.data_ptr() + 4 * lo, self.fp.flat.data_ptr() + 4 * self.fp.total)
+                self.opt.begin_step()
+                self.opt.apply_range(0, lo, 1.0 / self.world)
+                self._repack(rng, inside=False)
+                torch.cuda.current_stream().wait_stream(self._side)
+                self.opt.apply_range(lo, self.fp.total, 1.0 / self.world)
+                self._repack(rng, inside=True)
+            else:
+                self.opt.step(grad_scale=1.0 / self.world)
+                self._repack()
             self.fp.attach_grads()
         else:
             (loss / self.accum).backward()
@@ -338,12 +388,12 @@ class DataParallelTrainer:
             metrics = self.metrics_fn(logits.detach(), y) if self.metrics_fn is not None else None
         return loss.detach(), metrics
 
-    def _repack(self):
+    def _repack(self, ptr_range=None, inside=True):
         # the conv kernels' bf16 weight layouts follow the new fp32 parameters: one batched kernel per step
         # (functional.repack_cached_weights) instead of one pack kernel per layer and direction
         if self.fp.flat.is_cuda:
             from . import functional as F
-            F.repack_cached_weights()
+            F.repack_cached_weights(ptr_range, inside)
 
     def step(self, x, y):
         """Eager step on device tensors."""

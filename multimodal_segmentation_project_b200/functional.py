@@ -109,7 +109,7 @@ class _ToChannelsLast(torch.autograd.Function):
 # rewrites every cached layout in place (stable addresses: safe inside a captured CUDA graph).
 _weights_epoch = 0
 _pack_cache = {}          # (id(param), mode) -> dict(ref, packed, ptr, version, epoch, Cout, Cin)
-_pack_jobs = None         # (key tuple, device job table, njobs, total_groups)
+_pack_job_tables = {}     # subset tag -> (key tuple, device job table, njobs, total_groups)
 
 
 def weights_changed() -> None:
@@ -133,7 +133,6 @@ def pack_conv3_weights(weight: torch.Tensor, mode: int, dtype: torch.dtype) -> t
         out = torch.empty(L.b200_pack_conv3_bytes(mode, dt, Cout, Cin), dtype=torch.uint8, device=w.device)
         _pack_now(L, w, mode, dt, out, Cout, Cin)
         return out
-    global _pack_jobs
     key = (id(weight), mode)
     e = _pack_cache.get(key)
     if e is not None and (e["ref"]() is not weight or e["ptr"] != weight.data_ptr()):
@@ -143,22 +142,28 @@ def pack_conv3_weights(weight: torch.Tensor, mode: int, dtype: torch.dtype) -> t
         e = {"ref": weakref.ref(weight, lambda _r, k=key: _pack_cache.pop(k, None)), "packed": out, "ptr": weight.data_ptr(), "version": None,
              "epoch": None, "Cout": Cout, "Cin": Cin, "mode": mode}
         _pack_cache[key] = e
-        _pack_jobs = None
+        _pack_job_tables.clear()
     if e["version"] != weight._version or e["epoch"] != _weights_epoch:
         _pack_now(L, weight.detach(), mode, dt, e["packed"], Cout, Cin)
         e["version"], e["epoch"] = weight._version, _weights_epoch
     return e["packed"]
 
 
-def repack_cached_weights() -> int:
+def repack_cached_weights(ptr_range=None, inside=True) -> int:
     """Rewrites every cached packed layout from its parameter's CURRENT values in one kernel launch and marks the entries fresh.
-    Returns the number of layouts written (0 = nothing cached yet, no launch)."""
-    global _pack_jobs
+    ptr_range = (lo, hi): only the parameters whose storage starts inside (inside=True) or outside (inside=False) that address
+    range — a trainer repacks the buckets it has already stepped while the last bucket's all-reduce is in flight.
+    Returns the number of layouts written (0 = nothing to do, no launch)."""
     L = _lib.load()
     live = [(k, e) for k, e in _pack_cache.items() if e["ref"]() is not None]
+    if ptr_range is not None:
+        lo, hi = ptr_range
+        live = [(k, e) for k, e in live if (lo <= e["ptr"] < hi) == bool(inside)]
     if not live:
         return 0
+    tag = None if ptr_range is None else (ptr_range[0], ptr_range[1], bool(inside))
     sig = tuple((k, e["ptr"], e["packed"].data_ptr()) for k, e in live)
+    _pack_jobs = _pack_job_tables.get(tag)
     if _pack_jobs is None or _pack_jobs[0] != sig:
         import struct
         buf, g = bytearray(), 0
@@ -168,7 +173,7 @@ def repack_cached_weights() -> int:
         buf += struct.pack("<QQiiiiq", 0, 0, 0, 0, 0, 0, g)
         dev = live[0][1]["packed"].device
         table = torch.frombuffer(buf, dtype=torch.uint8).clone().to(dev)
-        _pack_jobs = (sig, table, len(live), g)
+        _pack_jobs = _pack_job_tables[tag] = (sig, table, len(live), g)
     _, table, n, total = _pack_jobs
     check(L.b200_pack_conv3_batched(_ptr(table), n, total, _stream()), "pack_conv3_batched")
     for _, e in live:
@@ -333,6 +338,16 @@ def set_deferred_wgrad_join(on: bool) -> None:
     global _defer_join
     join_pending()
     _defer_join = bool(on)
+
+
+def order_after_pending(stream) -> None:
+    """Orders `stream` after every outstanding side-stream weight gradient WITHOUT joining them into the current stream (the held
+    tensors stay held): a communication stream that must see a bucket's gradients while the main chain runs on."""
+    seen = set()
+    for side, _, _ in _pending:
+        if id(side) not in seen:
+            seen.add(id(side))
+            stream.wait_stream(side)
 
 
 def join_pending() -> None:
@@ -1181,16 +1196,33 @@ class FlatAdamW(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
+        self.begin_step()
+        self.apply_range(0, self.p.numel(), grad_scale)
+
+    @torch.no_grad()
+    def begin_step(self):
+        """Advances the step counter and the bias corrections once per optimiser step; follow with apply_range() calls that
+        together cover the flat buffer (a trainer steps the buckets whose all-reduce has finished while the last is in flight)."""
         L = _lib.load()
         self.sync_hyper()
         g = self.param_groups[0]
         check(L.b200_adamw_prepare(_ptr(self.step_count), g["betas"][0], g["betas"][1], _ptr(self.hyper), _stream()), "adamw_prepare")
+        weights_changed()       # parameters are about to be written through raw pointers: cached packed layouts go stale ONCE per step
+
+    @torch.no_grad()
+    def apply_range(self, lo: int, hi: int, grad_scale: float = 1.0):
+        """AdamW update of flat elements [lo, hi); lo must be a multiple of 4 (16-byte aligned slices)."""
+        if hi <= lo:
+            return
+        if lo % 4:
+            raise ValueError(f"FlatAdamW.apply_range: lo={lo} must be a multiple of 4")
+        L = _lib.load()
+        g = self.param_groups[0]
         check(
-            L.b200_adamw_flat(_ptr(self.p), _ptr(self.g), _ptr(self.m), _ptr(self.v), self.p.numel(), _ptr(self.hyper),
+            L.b200_adamw_flat(_ptr(self.p[lo:hi]), _ptr(self.g[lo:hi]), _ptr(self.m[lo:hi]), _ptr(self.v[lo:hi]), hi - lo, _ptr(self.hyper),
                               g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], float(grad_scale), _stream()),
             "adamw_flat",
         )
-        weights_changed()       # parameters were written through raw pointers: cached packed layouts are stale
 
     # ---- torch.optim.AdamW wire format ------------------------------------------------------------------------------
     def _slices(self):
