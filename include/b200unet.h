@@ -189,6 +189,12 @@ int b200_channel_sum(int dtype, const void* x, int64_t M, int C, float* partials
 /* ---------------------------------------------------------------- MaxPool3d(2,2)  models/unet.py:40,71 */
 int b200_maxpool2_fwd(int dtype, const void* x, void* y, int N, int D, int H, int W, int C, void* stream);
 /* gradient goes to the first maximum in (d,h,w) scan order, as ATen's max_pool3d_with_indices */
+/* BatchNorm3d + ReLU apply and MaxPool3d(2,2) of the result in ONE pass (models/unet.py:16-18 feeding :69-71: the encoder
+ * hand-off): y [N,D,H,W,C] and pooled [N,D/2,H/2,W/2,C] from the pre-BN tensor x; element arithmetic of b200_bn_act_fwd
+ * (relu = 1, no Dropout3d mask) and b200_maxpool2_fwd.  Needs even D/H/W and C/8 dividing 256 (b200_bn_act_pool_fwd_supported). */
+int b200_bn_act_pool_fwd_supported(int D, int H, int W, int C);
+int b200_bn_act_pool_fwd(int dtype, const void* x, void* y, void* pooled, const float* scale, const float* shift, const float* mean,
+                         int N, int D, int H, int W, int C, void* stream);
 int b200_maxpool2_bwd(int dtype, const void* x, const void* gy, void* gx, int N, int D, int H, int W, int C, void* stream);
 /* the encoder output feeds both the pool and the decoder's skip connection (models/unet.py:69-71,84): gx = gskip + scatter(gy)
  * in one pass instead of the pool backward followed by autograd's accumulation kernel */

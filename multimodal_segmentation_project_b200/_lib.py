@@ -76,6 +76,8 @@ def _declare(lib) -> None:
         "b200_channel_sum": (I, [I, P, L, I, P, P, P]),
         "b200_maxpool2_fwd": (I, [I, P, P, I, I, I, I, I, P]),
         "b200_maxpool2_bwd": (I, [I, P, P, P, I, I, I, I, I, P]),
+        "b200_bn_act_pool_fwd_supported": (I, [I, I, I, I]),
+        "b200_bn_act_pool_fwd": (I, [I, P, P, P, P, P, P, I, I, I, I, I, P]),
         "b200_ct_window": (I, [P, P, L, F, F, P]),
         "b200_preprocess_workspace_bytes": (L, []),
         "b200_moments_f32": (I, [P, L, P, P, P]),

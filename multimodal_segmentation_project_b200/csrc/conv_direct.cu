@@ -562,7 +562,7 @@ static int convt_tc_enabled() {
 }
 bool b200_convt2_wgrad_tc_supported(int Cin, int Cout, int N, int D, int H, int W);
 int64_t b200_convt2_wgrad_tc_workspace(int Cin, int Cout, int N, int D, int H, int W);
-int b200_convt2_wgrad_tc(const void* x, const void* gy, float* dw, void* workspace, int N, int D, int H, int W, int Cin, int Cout, cudaStream_t stream);
+int b200_convt2_wgrad_tc(const void* x, const void* gy, float* dw, float* dbias, void* workspace, int N, int D, int H, int W, int Cin, int Cout, cudaStream_t stream);
 // wide-row variant (wgrad_tc3.cu): 32-channel operand rows for layers with >= 32 channels on both sides
 bool b200_conv3d_wgrad_tc3_supported(int c0, int c1, int Cout, int N, int D, int H, int W);
 int64_t b200_conv3d_wgrad_tc3_workspace(int c0, int c1, int Cout, int N, int D, int H, int W);
@@ -889,8 +889,8 @@ extern "C" int b200_convt2_bwd_weight(int dtype, const void* x, const void* gy, 
   float* partial = (float*)((uint8_t*)workspace + b200_bn_partials_bytes(((Cout + 7) / 8) * 8));
   int rc;
   if (dtype == B200_BF16 && g_wgrad_impl != 1 && b200_convt2_wgrad_tc_supported(Cin, Cout, N, D, H, W)) {
-    rc = b200_convt2_wgrad_tc(x, gy, dw, partial, N, D, H, W, Cin, Cout, st);
-    if (rc) return rc;
+    // the bias gradient rides on the kernel (column sums of the staged gy planes)
+    return b200_convt2_wgrad_tc(x, gy, dw, dbias, partial, N, D, H, W, Cin, Cout, st);
   } else {
     const SplitPlan sp = plan_split(M, Cin, 8 * Cout);
     if (dtype == B200_F32) {

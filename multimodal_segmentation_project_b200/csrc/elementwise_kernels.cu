@@ -430,6 +430,62 @@ maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int D, in
   }
 }
 
+// BatchNorm + ReLU apply AND MaxPool3d(2,2) of the result in one pass (the encoder hand-off, models/unet.py:16-18 feeding :69-71):
+// one thread owns a 2x2x2 window of an 8-channel group, reads the pre-BN tensor once, writes the activation and the pooled
+// tensor — the separate pool pass re-read the 134 MB activation it had just written.  Element arithmetic = bn_act_fwd_kernel's
+// (no Dropout3d here: the caller keeps the two-pass sequence when a mask is present) and maxpool2_fwd_kernel's.  Even D, H, W.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+bn_act_pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ pooled, const float* __restrict__ scale,
+                       const float* __restrict__ shift, const float* __restrict__ mean, int N, int D, int H, int W, int C) {
+  const int OD = D / 2, OH = H / 2, OW = W / 2, CV = C / 8;
+  const int cv = threadIdx.x % CV;            // blockDim.x and the grid stride are multiples of CV: a thread keeps its channel group
+  float sc[8], sh[8], mu[8];
+  load8(scale, cv, sc); load8(shift, cv, sh); load8(mean, cv, mu);
+  const int64_t total = (int64_t)N * OD * OH * OW * CV;
+  const bool small = total < (1ll << 31);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int ow, oh, od, n;
+    if (small) {   // 32-bit index arithmetic whenever the tensor allows it
+      uint32_t t = (uint32_t)i / (uint32_t)CV;
+      ow = (int)(t % (uint32_t)OW); t /= (uint32_t)OW;
+      oh = (int)(t % (uint32_t)OH); t /= (uint32_t)OH;
+      od = (int)(t % (uint32_t)OD);
+      n = (int)(t / (uint32_t)OD);
+    } else {
+      int64_t t = i / CV;
+      ow = (int)(t % OW); t /= OW;
+      oh = (int)(t % OH); t /= OH;
+      od = (int)(t % OD);
+      n = (int)(t / OD);
+    }
+    const int64_t row0 = (((int64_t)n * D + 2 * od) * H + 2 * oh) * W + 2 * ow;
+    Vec8<T> v[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) v[p].load(x + (row0 + ((int64_t)(p >> 2) * H + ((p >> 1) & 1)) * W + (p & 1)) * C + cv * 8);
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      float f[8];
+      v[p].get(f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float t = fmaxf(to_f32<T>(from_f32<T>(fmaf(f[k] - mu[k], sc[k], sh[k]))), 0.f);
+        f[k] = t;
+        if (pool_better(t, m[k])) m[k] = t;
+      }
+      Vec8<T> o;
+      o.set(f);
+      o.store(y + (row0 + ((int64_t)(p >> 2) * H + ((p >> 1) & 1)) * W + (p & 1)) * C + cv * 8);
+    }
+    Vec8<T> po;
+    po.set(m);
+    po.store(pooled + ((((int64_t)n * OD + od) * OH + oh) * OW + ow) * C + cv * 8);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy, const T* __restrict__ gskip, T* __restrict__ gx, int N, int D, int H, int W,
@@ -962,6 +1018,24 @@ extern "C" int b200_maxpool2_fwd(int dtype, const void* x, void* y, int N, int D
   const int64_t items = (int64_t)N * (D / 2) * (H / 2) * (W / 2) * (C / 8);
   B200_DISPATCH_DTYPE(dtype, T, (maxpool2_fwd_kernel<T><<<ew_grid(items), kThreads, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, N, D, H, W, C)));
   B200_CHECK_LAUNCH("maxpool2_fwd");
+  return B200_OK;
+}
+
+// y = relu(bn(x)) and pooled = MaxPool3d(2,2)(y) in one pass; D, H, W even and C/8 dividing the block size (else: bn_act_fwd + maxpool2_fwd)
+extern "C" int b200_bn_act_pool_fwd_supported(int D, int H, int W, int C) {
+  const int CV = C / 8;
+  return C % 8 == 0 && CV >= 1 && kThreads % CV == 0 && D >= 2 && H >= 2 && W >= 2 && ((D | H | W) & 1) == 0;
+}
+extern "C" int b200_bn_act_pool_fwd(int dtype, const void* x, void* y, void* pooled, const float* scale, const float* shift, const float* mean,
+                                    int N, int D, int H, int W, int C, void* stream) {
+  int rc = check_rows("bn_act_pool_fwd", (int64_t)N * D * H * W, C);
+  if (rc) return rc;
+  B200_REQUIRE(b200_bn_act_pool_fwd_supported(D, H, W, C), B200_ERR_UNSUPPORTED, "bn_act_pool_fwd: needs even D/H/W and C/8 dividing %d (C=%d, %dx%dx%d)", kThreads, C, D, H, W);
+  B200_REQUIRE(x && y && pooled && scale && shift && mean, B200_ERR_SHAPE, "bn_act_pool_fwd: null pointer");
+  const int64_t items = (int64_t)N * (D / 2) * (H / 2) * (W / 2) * (C / 8);
+  B200_DISPATCH_DTYPE(dtype, T, (bn_act_pool_fwd_kernel<T><<<b200_grid_for(items, kThreads, B200_NUM_SMS * 4), kThreads, 0, (cudaStream_t)stream>>>(
+                                    (const T*)x, (T*)y, (T*)pooled, scale, shift, mean, N, D, H, W, C)));
+  B200_CHECK_LAUNCH("bn_act_pool_fwd");
   return B200_OK;
 }
 

@@ -271,6 +271,7 @@ struct CtParams {
   const bf16* gy; int cout;   // fine grid [N,2D,2H,2W,cout]
   int cin;
   float* partial;             // [cta][mrows][128]
+  float* bias_partial;        // [qslab][spatial cta][16] per-CTA sums of gy over voxels and children (NULL: no bias gradient)
   int mrows, mslabs;
   int N, D, H, W;             // coarse geometry
   int dseg, dblocks, tiles_w, tiles_h;
@@ -291,6 +292,7 @@ convt_wgrad_tc_kernel(const CtParams g, const __grid_constant__ CUtensorMap tm_x
   const uint32_t p_stage_bytes = (uint32_t)g.mslabs * kPSlabBytes;
   uint8_t* pbuf = smem + kHeader;
   uint8_t* qbuf = pbuf + kCtStages * p_stage_bytes;
+  float* bsum = reinterpret_cast<float*>(qbuf + kCtStages * kCtQBytes);   // [4 warps][16] column sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tw = blockIdx.x % g.tiles_w, th = blockIdx.x / g.tiles_w % g.tiles_h;
@@ -302,7 +304,7 @@ convt_wgrad_tc_kernel(const CtParams g, const __grid_constant__ CUtensorMap tm_x
 
   if (warp == 8 && lane == 0) {
     for (int i = 0; i < kCtStages; ++i) {
-      tc::mbar_init(q_full(i), 1); tc::mbar_init(q_empty(i), 1);
+      tc::mbar_init(q_full(i), 1); tc::mbar_init(q_empty(i), 1 + 4);   // released by the MMA commit AND the four column-sum warps
       tc::mbar_init(p_full(i), 1); tc::mbar_init(p_empty(i), 1);
     }
     tc::mbar_init(acc_done, 1);
@@ -339,6 +341,54 @@ convt_wgrad_tc_kernel(const CtParams g, const __grid_constant__ CUtensorMap tm_x
         tc::mbar_arrive_expect_tx(p_full(st), p_stage_bytes);
         for (int ms = 0; ms < g.mslabs; ++ms)
           tma::load_5d(tc::smem_u32(pbuf + st * p_stage_bytes + ms * kPSlabBytes), &tm_x, mchunk * 64 + ms * 16, w0, h0, d, n, p_full(st));
+      }
+    }
+  } else if (warp < 4) {
+    // ---- bias gradient of the up-convolution = column sums of gy (models/unet.py:56-58: ConvTranspose3d has a bias): the staged
+    // child planes are in shared memory anyway, so warps 0-3 add them up instead of a separate 134 MB pass over gy
+    // (channel_sum_kernel: 32 us at the top level).  Thread t owns 16-byte chunk c = t & 1 (8 channels) of voxels (t >> 1) + 64 j.
+    const int tid = threadIdx.x, c = tid & 1;
+    const bool sum_here = g.bias_partial != nullptr && mchunk == 0;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int i = 0; i < planes; ++i) {
+      const int st = i % kCtStages;
+      tc::mbar_wait(q_full(st), (i / kCtStages) & 1);
+      if (sum_here) {
+        const uint8_t* src = qbuf + st * kCtQBytes;
+#pragma unroll
+        for (int child = 0; child < 8; ++child)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int v = (tid >> 1) + 64 * j;
+            const uint4 q = *reinterpret_cast<const uint4*>(src + child * kPSlabBytes + swz32((uint32_t)v * 32 + c * 16));
+            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              acc[2 * k] += __uint_as_float(w4[k] << 16);
+              acc[2 * k + 1] += __uint_as_float(w4[k] & 0xffff0000u);
+            }
+          }
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(q_empty(st));
+    }
+    if (sum_here) {
+      // fixed-shape fold: lanes of equal chunk parity inside the warp, then the four warps in order
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int o = 2; o < 32; o <<= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+      }
+      if (lane < 2) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bsum[warp * 16 + c * 8 + k] = acc[k];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // warps 0-3 only
+      if (tid < 16) {
+        const float t = ((bsum[tid] + bsum[16 + tid]) + bsum[32 + tid]) + bsum[48 + tid];
+        g.bias_partial[((int64_t)qslab * gridDim.x + blockIdx.x) * 16 + tid] = t;
       }
     }
   } else if (warp == 8) {
@@ -402,6 +452,15 @@ struct CtMap {
   }
 };
 
+// bias_partial[qslab][spatial][16] -> db[co]
+struct CtBiasMap {
+  int Cout;
+  __device__ int64_t operator()(int group, int64_t e) const {
+    const int co = group * 16 + (int)e;
+    return co < Cout ? co : -1;
+  }
+};
+
 struct CtPlan { int mslabs, mchunks, qslabs, mrows, dseg, dblocks, tiles_w, tiles_h, spatial; size_t smem; };
 CtPlan make_ct_plan(int Cin, int Cout, int N, int D, int H, int W) {
   CtPlan pl;
@@ -426,7 +485,7 @@ CtPlan make_ct_plan(int Cin, int Cout, int N, int D, int H, int W) {
   pl.dseg = dseg;
   pl.dblocks = (D + dseg - 1) / dseg;
   pl.spatial = pl.tiles_w * pl.tiles_h * N * pl.dblocks;
-  pl.smem = kHeader + (size_t)kCtStages * (pl.mslabs * kPSlabBytes + kCtQBytes) + 1024;
+  pl.smem = kHeader + (size_t)kCtStages * (pl.mslabs * kPSlabBytes + kCtQBytes) + 256 + 1024;
   return pl;
 }
 
@@ -438,15 +497,17 @@ bool b200_convt2_wgrad_tc_supported(int Cin, int Cout, int N, int D, int H, int 
 }
 int64_t b200_convt2_wgrad_tc_workspace(int Cin, int Cout, int N, int D, int H, int W) {
   const CtPlan pl = make_ct_plan(Cin, Cout, N, D, H, W);
-  return (int64_t)pl.spatial * pl.mchunks * pl.qslabs * pl.mrows * 128 * 4;
+  return (int64_t)pl.spatial * pl.mchunks * pl.qslabs * pl.mrows * 128 * 4 + (int64_t)pl.spatial * pl.qslabs * 16 * 4;
 }
-int b200_convt2_wgrad_tc(const void* x, const void* gy, float* dw, void* workspace, int N, int D, int H, int W, int Cin, int Cout,
+// dbias (optional): the bias gradient sum_v gy[v][co], taken from the child planes the kernel stages anyway
+int b200_convt2_wgrad_tc(const void* x, const void* gy, float* dw, float* dbias, void* workspace, int N, int D, int H, int W, int Cin, int Cout,
                          cudaStream_t stream) {
   B200_REQUIRE(b200_convt2_wgrad_tc_supported(Cin, Cout, N, D, H, W), B200_ERR_UNSUPPORTED, "convt2_wgrad(tcgen05): unsupported channel counts");
   const CtPlan pl = make_ct_plan(Cin, Cout, N, D, H, W);
   CtParams g;
   g.gy = (const bf16*)gy; g.cout = Cout; g.cin = Cin;
   g.partial = (float*)workspace; g.mrows = pl.mrows; g.mslabs = pl.mslabs;
+  g.bias_partial = dbias ? (float*)workspace + (int64_t)pl.spatial * pl.mchunks * pl.qslabs * pl.mrows * 128 : nullptr;
   g.N = N; g.D = D; g.H = H; g.W = W;
   g.dseg = pl.dseg; g.dblocks = pl.dblocks; g.tiles_w = pl.tiles_w; g.tiles_h = pl.tiles_h;
   CUtensorMap tm_x, tm_gy;
@@ -464,6 +525,10 @@ int b200_convt2_wgrad_tc(const void* x, const void* gy, float* dw, void* workspa
   B200_CHECK_LAUNCH("convt2_wgrad_tc");
   launch_partial_reduce((const float*)workspace, pl.spatial, (int64_t)pl.mrows * 128, pl.qslabs * pl.mchunks, CtMap{pl.mchunks, Cin, Cout}, dw, stream);
   B200_CHECK_LAUNCH("convt2_wgrad_tc_reduce");
+  if (dbias) {
+    launch_partial_reduce((const float*)g.bias_partial, pl.spatial, (int64_t)16, pl.qslabs, CtBiasMap{Cout}, dbias, stream);
+    B200_CHECK_LAUNCH("convt2_wgrad_tc_bias_reduce");
+  }
   return B200_OK;
 }
 

@@ -451,11 +451,18 @@ class _ConvBNAct(torch.autograd.Function):
                 "bn_finalize",
             )
         y = torch.empty_like(conv_out)
-        check(
-            L.b200_bn_act_fwd(_dt(conv_out), _ptr(conv_out), _ptr(y), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]), _ptr(dropmask), 1, N, S,
-                              Cout, _stream()),
-            "bn_act_fwd",
-        )
+        if getattr(ctx, "_b200_want_pool", False):
+            # _ConvBNActSkipPool: the apply pass also writes MaxPool3d(2,2)(y) (one read of conv_out, no re-read of y)
+            pooled = torch.empty((N, D // 2, H // 2, W // 2, Cout), dtype=y.dtype, device=dev)
+            check(L.b200_bn_act_pool_fwd(_dt(conv_out), _ptr(conv_out), _ptr(y), _ptr(pooled), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]),
+                                         N, D, H, W, Cout, _stream()), "bn_act_pool_fwd")
+            ctx._b200_pooled = pooled
+        else:
+            check(
+                L.b200_bn_act_fwd(_dt(conv_out), _ptr(conv_out), _ptr(y), _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]), _ptr(dropmask), 1, N, S,
+                                  Cout, _stream()),
+                "bn_act_fwd",
+            )
         ctx.save_for_backward(x0, x1, weight, conv_out, stats, dropmask, prev_conv_out, prev_stats)
         ctx.training = bool(training)
         ctx.has_bias = bias is not None
@@ -468,7 +475,7 @@ class _ConvBNAct(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy, _gconv=None, _gstats=None):
         L = _lib.load()
-        x0, x1, weight, conv_out, stats, dropmask, prev_conv_out, prev_stats = ctx.saved_tensors
+        x0, x1, weight, conv_out, stats, dropmask, prev_conv_out, prev_stats = ctx.saved_tensors[:8]
         if gy is None:                        # (materialize_grads is off) nothing flows back through this block
             return (None,) * 16
         _run_bwd_callback(weight.data_ptr())
@@ -795,6 +802,67 @@ class _SkipPool(torch.autograd.Function):
 def skip_and_pool(x):
     """(skip, pooled) = (x, maxpool2(x)) with a fused backward."""
     return _SkipPool.apply(x)
+
+
+_fuse_pool_fwd = os.environ.get("B200_FUSE_POOL_FWD", "1") != "0"
+
+
+def set_fuse_pool_fwd(on: bool) -> None:
+    """Encoder hand-off forward: BatchNorm apply + MaxPool3d in one pass (default) or bn_act_fwd followed by maxpool2_fwd."""
+    global _fuse_pool_fwd
+    _fuse_pool_fwd = bool(on)
+
+
+def bn_pool_fusable(x0, out_channels: int, dropmask) -> bool:
+    """True if conv_bn_act_skip_pool serves a layer with input x0 [N, D, H, W, C] (even sizes, no Dropout3d mask)."""
+    if not _fuse_pool_fwd or dropmask is not None or not x0.is_cuda or x0.dim() != 5:
+        return False
+    _, D, H, W, _ = x0.shape
+    return bool(_lib.load().b200_bn_act_pool_fwd_supported(D, H, W, out_channels))
+
+
+class _ConvBNActSkipPool(torch.autograd.Function):
+    """_ConvBNAct followed by the encoder hand-off (skip, MaxPool3d(2,2)) — models/unet.py:15-18 feeding :69-71 — as ONE autograd
+    node: the BatchNorm apply pass writes the pooled tensor as well (csrc/elementwise_kernels.cu, bn_act_pool_fwd_kernel), so the
+    activation is not re-read by a separate pool pass.  Backward: maxpool2_bwd_add joins the two incoming gradients (as _SkipPool
+    does), then _ConvBNAct's backward.  Same arithmetic as the two-node sequence, bit for bit."""
+
+    @staticmethod
+    def forward(ctx, *args):
+        ctx._b200_want_pool = True
+        y, conv_out, stats = _ConvBNAct.forward(ctx, *args)
+        pooled = ctx._b200_pooled
+        ctx._b200_pooled = None
+        # the pool backward routes by the arg-max of y: saved as a ninth tensor (an output, alive as the skip connection anyway)
+        ctx.save_for_backward(*ctx.to_save, y)
+        return y, pooled, conv_out, stats
+
+    @staticmethod
+    def backward(ctx, g_skip, g_pool, _gconv=None, _gstats=None):
+        if g_pool is None:
+            return _ConvBNAct.backward(ctx, g_skip)
+        L = _lib.load()
+        y = ctx.saved_tensors[8]
+        N, D, H, W, C = y.shape
+        g_pool = g_pool.contiguous()
+        gy = torch.empty_like(y)
+        if g_skip is None:
+            check(L.b200_maxpool2_bwd(_dt(y), _ptr(y), _ptr(g_pool), _ptr(gy), N, D, H, W, C, _stream()), "maxpool2_bwd")
+        else:
+            g_skip = g_skip.contiguous()
+            check(L.b200_maxpool2_bwd_add(_dt(y), _ptr(y), _ptr(g_pool), _ptr(g_skip), _ptr(gy), N, D, H, W, C, _stream()), "maxpool2_bwd_add")
+        return _ConvBNAct.backward(ctx, gy)
+
+
+def conv_bn_act_skip_pool(x0, x1, conv, bn, training, impl=0, prev=None):
+    """(skip, pooled) = skip_and_pool(conv_bn_act(...)) with the pooled tensor written by the BatchNorm apply pass; call only when
+    bn_pool_fusable() holds."""
+    if bn.momentum is None:
+        raise ValueError("BatchNorm3d(momentum=None) (cumulative moving average) is not supported by libb200unet")
+    pco, pst = prev if prev is not None else (None, None)
+    y, pooled, _, _ = _ConvBNActSkipPool.apply(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                               bn.num_batches_tracked, None, training, bn.eps, bn.momentum, impl, pco, pst)
+    return y, pooled
 
 
 # --------------------------------------------------------------------------- ConvTranspose3d(k2,s2)

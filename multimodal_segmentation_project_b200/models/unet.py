@@ -47,10 +47,12 @@ class DoubleConv(nn.Module):
             return torch.zeros((n, c), dtype=torch.float32, device=device)
         return torch.empty((n, c), dtype=torch.float32, device=device).bernoulli_(1.0 - p).div_(1.0 - p)
 
-    def forward_cl(self, x0, x1=None, impl=0, defer_last_norm=False):
+    def forward_cl(self, x0, x1=None, impl=0, defer_last_norm=False, pool=False):
         """Channels-last forward; ``x1`` is the second half of a virtual concat (skip first).
         ``defer_last_norm``: stop after the second convolution and its batch statistics and return ``(conv_out, stats)`` — the
-        caller (the fused head) applies BatchNorm + ReLU on the fly instead of materialising them."""
+        caller (the fused head) applies BatchNorm + ReLU on the fly instead of materialising them.
+        ``pool``: return ``(skip, MaxPool3d(2,2)(skip))`` — the encoder hand-off (reference models/unet.py:69-71) as part of the
+        block: the last BatchNorm apply pass then writes the pooled tensor too."""
         seq = self.double_conv
         n = x0.shape[0]
         m0 = self._mask(seq[3], n, seq[0].out_channels, x0.device)
@@ -61,6 +63,11 @@ class DoubleConv(nn.Module):
         if defer_last_norm:
             return F.conv_batch_stats(h, None, seq[4], seq[5], impl, prev=prev)
         m1 = self._mask(seq[7], n, seq[4].out_channels, x0.device)
+        if pool:
+            if F.bn_pool_fusable(h, seq[4].out_channels, m1):
+                return F.conv_bn_act_skip_pool(h, None, seq[4], seq[5], seq[5].training, impl, prev=prev)
+            # skip connection + MaxPool3d(2,2); their gradients meet in one kernel
+            return F.skip_and_pool(F.conv_bn_act(h, None, seq[4], seq[5], m1, seq[5].training, impl, prev=prev))
         return F.conv_bn_act(h, None, seq[4], seq[5], m1, seq[5].training, impl, prev=prev)
 
     def forward(self, x):
@@ -138,8 +145,7 @@ class UNet3D(nn.Module):
         h = F._ToChannelsLast.apply(x, dtype)
         skips = []
         for down in self.encoder:
-            h = down.forward_cl(h, None, impl)
-            skip, h = F.skip_and_pool(h)  # skip connection + MaxPool3d(2,2); their gradients meet in one kernel
+            skip, h = down.forward_cl(h, None, impl, pool=True)  # skip connection + MaxPool3d(2,2)
             skips.append(skip)
         bott = self.bottleneck.forward_cl(h, None, impl)
         h = bott

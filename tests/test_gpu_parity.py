@@ -279,6 +279,42 @@ def test_maxpool_fwd_bwd(cuda_dev, dtype, shape):
     assert torch.equal(cf(xs2.grad), xr.grad)
 
 
+@pytest.mark.parametrize("case", [(2, 16, 16, 8, 12, 16, True, torch.bfloat16), (1, 16, 32, 6, 8, 10, True, torch.bfloat16),
+                                  (2, 32, 64, 4, 4, 6, True, torch.float32), (1, 16, 16, 8, 8, 8, False, torch.bfloat16),
+                                  (1, 64, 128, 2, 4, 4, True, torch.bfloat16), (1, 8, 24, 4, 6, 6, True, torch.float32)])
+def test_encoder_handoff_fused_forward_is_bit_identical(cuda_dev, case):
+    """DoubleConv -> (skip, MaxPool3d) — models/unet.py:69-71: BatchNorm apply + pool in one pass (bn_act_pool_fwd_kernel) against
+    bn_act_fwd followed by maxpool2_fwd: same element arithmetic, so outputs and every gradient are bit-identical."""
+    N, Cin, Cout, D, H, W, use_skip, dtype = case
+    torch.manual_seed(3)
+    blk = DoubleConv(Cin, Cout, dropout_rate=0.0).to(cuda_dev).train()
+    x = torch.randn(N, D, H, W, Cin, device=cuda_dev).to(dtype)
+    g_skip = torch.randn(N, D, H, W, Cout, device=cuda_dev).to(dtype)
+    g_pool = torch.randn(N, D // 2, H // 2, W // 2, Cout, device=cuda_dev).to(dtype)
+    res = []
+    try:
+        for fused in (True, False):
+            F.set_fuse_pool_fwd(fused)
+            blk.zero_grad(set_to_none=True)
+            xi = x.clone().requires_grad_(True)
+            n0 = _lib.launch_count()
+            skip, pooled = blk.forward_cl(xi, None, 0, pool=True)
+            # 24 channels = three 8-channel groups do not divide the 256-thread block: that case keeps the two-pass sequence
+            assert type(skip.grad_fn).__name__.startswith("_ConvBNActSkipPool") == (fused and 256 % (Cout // 8) == 0)
+            if use_skip:
+                torch.autograd.backward([skip, pooled], [g_skip, g_pool])
+            else:
+                pooled.backward(g_pool)
+            torch.cuda.synchronize()
+            assert _lib.launch_count() > n0
+            res.append((skip.detach().clone(), pooled.detach().clone(), xi.grad.clone(), {k: v.grad.clone() for k, v in blk.named_parameters() if v.grad is not None}))
+    finally:
+        F.set_fuse_pool_fwd(True)
+    (s1, p1, gx1, gp1), (s2, p2, gx2, gp2) = res
+    assert torch.equal(s1, s2) and torch.equal(p1, p2) and torch.equal(gx1, gx2)
+    assert gp1.keys() == gp2.keys() and all(torch.equal(gp1[k], gp2[k]) for k in gp1)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(2, 32, 16, 3, 4, 5), (1, 256, 128, 2, 2, 2), (1, 64, 32, 5, 17, 20), (2, 128, 64, 3, 16, 9)])
 def test_conv_transpose_fwd_bwd(cuda_dev, dtype, shape):
