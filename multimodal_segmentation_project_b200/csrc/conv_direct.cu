@@ -578,7 +578,9 @@ static int g_inject_wgrad_failure = 0;  // tests: the next wide-row tcgen05 weig
 // in_channels == 1 first layer (conv_stem.cu)
 bool b200_conv_stem_supported(int c0, int c1, int cout);
 bool b200_conv_stem_wgrad_supported(int c0, int c1, int cout);
-int b200_conv_stem_fwd(int dtype, const void* x, const void* wpack, const float* bias, void* y, int cout, int N, int D, int H, int W, cudaStream_t st);
+int b200_conv_stem_fwd(int dtype, const void* x, const void* wpack, const float* bias, void* y, int cout, int N, int D, int H, int W, cudaStream_t st,
+                       float* stats = nullptr);
+int b200_conv_stem_stats_blocks(int dtype, int cout, int N, int D, int H, int W);
 int64_t b200_conv_stem_wgrad_workspace(int cout);
 int b200_conv_stem_wgrad(int dtype, const void* x, const void* dy, int cout, float* dw, float* partials, int N, int D, int H, int W, cudaStream_t st);
 
@@ -678,6 +680,7 @@ static bool conv_persistent_on(int c0, int c1, int co0, int co1) {
 // accumulates sum / sum of squares of (y - bias) per channel over the bf16 values it stores.  Returns the number of partial rows
 // written to `partials` ([rows][2][Cout] fp32, the layout of b200_bn_stats) — pass it, with shift = bias, to b200_bn_finalize_ex.
 extern "C" int b200_conv3d_k3_bnstats_blocks(int dtype, int impl, int c0, int c1, int co0, int co1, int N, int D, int H, int W) {
+  if (co1 == 0 && b200_conv_stem_supported(c0, c1, co0)) return b200_conv_stem_stats_blocks(dtype, co0, N, D, H, W);   // first layer (Cin = 1)
   if (dtype != B200_BF16 || impl != 2 || tc_version() != 2 || !b200_conv3d_k3_tc_supported(c0, c1, co0, co1, N, D, H, W)) return 0;
   if (!conv_persistent_on(c0, c1, co0, co1)) return 0;
   const int rows = b200_conv3d_k3_tc4_stats_blocks(c0, c1, co0, co1, N, D, H, W);
@@ -690,6 +693,8 @@ extern "C" int b200_conv3d_k3_bnstats(int dtype, int impl, const void* x0, int c
   B200_REQUIRE((c1 == 0) == (x1 == nullptr), B200_ERR_SHAPE, "conv3d_k3_bnstats: second tensor / channel count mismatch");
   B200_REQUIRE(b200_conv3d_k3_bnstats_blocks(dtype, impl, c0, c1, co0, 0, N, D, H, W) > 0, B200_ERR_UNSUPPORTED,
                "conv3d_k3_bnstats: the fused-statistics kernel does not serve this problem (ask b200_conv3d_k3_bnstats_blocks first)");
+  if (b200_conv_stem_supported(c0, c1, co0))
+    return b200_conv_stem_fwd(dtype, x0, wpack, bias, y0, co0, N, D, H, W, (cudaStream_t)stream, partials);
   if (b200_conv3d_k3_tc4_stats_blocks(c0, c1, co0, 0, N, D, H, W) > 0)
     return b200_conv3d_k3_tc4(x0, c0, x1, c1, wpack, bias, y0, co0, nullptr, 0, N, D, H, W, (cudaStream_t)stream, partials);
   return b200_conv3d_k3_tc3(x0, c0, x1, c1, wpack, bias, y0, co0, nullptr, 0, N, D, H, W, (cudaStream_t)stream, partials);

@@ -214,8 +214,11 @@ __device__ __forceinline__ void load_halo(uint16_t* xs, const bf16* __restrict__
 
 __global__ void __launch_bounds__(kMmaThreads)
 stem_fwd_mma_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wpack /*[27][16]*/, const float* __restrict__ bias,
-                    bf16* __restrict__ y, int N, int D, int H, int W, int tiles_w, int tiles_h, int tiles_d) {
+                    bf16* __restrict__ y, int N, int D, int H, int W, int tiles_w, int tiles_h, int tiles_d, float* __restrict__ stats) {
+  // stats (optional): per-CTA BatchNorm partial sums [block][2][16] of (stored output - bias) and its square — the contract of the
+  // tcgen05 kernels' fused statistics (conv_tc3 / conv_tc4), so that the separate 134 MB bn_stats pass over y disappears
   __shared__ uint16_t xs[XD * XH * XP];
+  __shared__ float sred[8][32];
   int r = blockIdx.x;
   const int tw = r % tiles_w; r /= tiles_w;
   const int th = r % tiles_h; r /= tiles_h;
@@ -247,11 +250,12 @@ stem_fwd_mma_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wpack /
   for (int nt = 0; nt < 2; ++nt) { bz[nt][0] = bias ? bias[nt * 8 + 2 * t] : 0.f; bz[nt][1] = bias ? bias[nt * 8 + 2 * t + 1] : 0.f; }
   __syncthreads();
   const int h = warp, gh = h0 + h;
-  if (gh >= H) return;
+  float ssum[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, ssq[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  if (gh >= H && !stats) return;
 #pragma unroll 2
   for (int mt = 0; mt < SD * 2; ++mt) {
     const int d = mt >> 1, wl = (mt & 1) * 16, gd = d0 + d;
-    if (gd >= D) break;
+    if (gd >= D || gh >= H) break;
     if (w0 + wl >= W) continue;
     const uint16_t* base = xs + (d * XH + h) * XP + wl + g;
     uint32_t a[2][4];
@@ -274,8 +278,41 @@ stem_fwd_mma_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wpack /
     bf16* yr = y + ((((int64_t)n * D + gd) * H + gh) * W + gw) * 16 + 2 * t;
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
-      if (gw < W) *reinterpret_cast<__nv_bfloat162*>(yr + nt * 8) = __floats2bfloat162_rn(c[nt][0], c[nt][1]);
-      if (gw + 8 < W) *reinterpret_cast<__nv_bfloat162*>(yr + 8 * 16 + nt * 8) = __floats2bfloat162_rn(c[nt][2], c[nt][3]);
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(c[nt][0], c[nt][1]), hi = __floats2bfloat162_rn(c[nt][2], c[nt][3]);
+      if (gw < W) *reinterpret_cast<__nv_bfloat162*>(yr + nt * 8) = lo;
+      if (gw + 8 < W) *reinterpret_cast<__nv_bfloat162*>(yr + 8 * 16 + nt * 8) = hi;
+      if (stats) {
+        const float2 l = __bfloat1622float2(lo), u = __bfloat1622float2(hi);
+        if (gw < W) {
+          const float e0 = l.x - bz[nt][0], e1 = l.y - bz[nt][1];
+          ssum[nt][0] += e0; ssq[nt][0] = fmaf(e0, e0, ssq[nt][0]);
+          ssum[nt][1] += e1; ssq[nt][1] = fmaf(e1, e1, ssq[nt][1]);
+        }
+        if (gw + 8 < W) {
+          const float e0 = u.x - bz[nt][0], e1 = u.y - bz[nt][1];
+          ssum[nt][0] += e0; ssq[nt][0] = fmaf(e0, e0, ssq[nt][0]);
+          ssum[nt][1] += e1; ssq[nt][1] = fmaf(e1, e1, ssq[nt][1]);
+        }
+      }
+    }
+  }
+  if (stats) {
+    // fixed-shape fold: the eight lanes that share t (xor 4, 8, 16), then the eight warps in order; channel = nt * 8 + 2 t + j
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float a = ssum[nt][j], b = ssq[nt][j];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        if (g == 0) { sred[warp][nt * 8 + 2 * t + j] = a; sred[warp][16 + nt * 8 + 2 * t + j] = b; }
+      }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float tot = 0.f;
+#pragma unroll
+      for (int wq = 0; wq < 8; ++wq) tot += sred[wq][threadIdx.x];
+      stats[(size_t)blockIdx.x * 32 + threadIdx.x] = tot;
     }
   }
 }
@@ -379,16 +416,27 @@ inline int wg_blocks(int N, int D, int H, int W) {
 bool b200_conv_stem_supported(int c0, int c1, int cout) { return c0 == 1 && c1 == 0 && (cout == 16 || cout == 32 || cout == 8); }
 bool b200_conv_stem_wgrad_supported(int c0, int c1, int cout) { return c0 == 1 && c1 == 0 && (cout == 16 || cout == 8); }
 
+// rows of fused BatchNorm partial sums the bf16 tensor-core stem kernel writes (0: that kernel does not serve the problem)
+int b200_conv_stem_stats_blocks(int dtype, int cout, int N, int D, int H, int W) {
+  if (dtype != B200_BF16 || cout != 16 || !stem_mma_enabled()) return 0;
+  static int on = -1;             // env B200_STEM_STATS=0: separate bn_stats pass (A/B knob)
+  if (on < 0) { const char* e = getenv("B200_STEM_STATS"); on = e ? atoi(e) : 1; }
+  if (!on) return 0;
+  const int64_t g = (int64_t)((W + SW - 1) / SW) * ((H + SH - 1) / SH) * ((D + SD - 1) / SD) * N;
+  return g < (1 << 20) ? (int)g : 0;
+}
+
 int b200_conv_stem_fwd(int dtype, const void* x, const void* wpack, const float* bias, void* y, int cout, int N, int D, int H, int W,
-                       cudaStream_t st) {
+                       cudaStream_t st, float* stats) {
   if (dtype == B200_BF16 && cout == 16 && stem_mma_enabled()) {
     const int tw = (W + SW - 1) / SW, th = (H + SH - 1) / SH, td = (D + SD - 1) / SD;
     const int64_t g = (int64_t)tw * th * td * N;
     B200_REQUIRE(g < 2147483647LL, B200_ERR_UNSUPPORTED, "conv_stem_fwd: volume too large");
-    stem_fwd_mma_kernel<<<(unsigned)g, kMmaThreads, 0, st>>>((const bf16*)x, (const bf16*)wpack, bias, (bf16*)y, N, D, H, W, tw, th, td);
+    stem_fwd_mma_kernel<<<(unsigned)g, kMmaThreads, 0, st>>>((const bf16*)x, (const bf16*)wpack, bias, (bf16*)y, N, D, H, W, tw, th, td, stats);
     B200_CHECK_LAUNCH("conv_stem_fwd_mma");
     return B200_OK;
   }
+  B200_REQUIRE(stats == nullptr, B200_ERR_UNSUPPORTED, "conv_stem_fwd: fused statistics need the bf16 16-channel tensor-core kernel");
   const int tiles_w = (W + FT_W - 1) / FT_W, tiles_h = (H + FT_H - 1) / FT_H;
   const int64_t grid = (int64_t)tiles_w * tiles_h * N * D;
   B200_REQUIRE(grid < 2147483647LL, B200_ERR_UNSUPPORTED, "conv_stem_fwd: volume too large");

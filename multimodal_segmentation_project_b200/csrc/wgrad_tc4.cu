@@ -57,7 +57,8 @@ constexpr size_t kSmemBytes = 1024 + (size_t)kPStages * kPBytes + (size_t)kQStag
 struct Wg4Params {
   float* partial;
   int N, D, H, W;
-  int dseg, dblocks, tiles_w, tiles_h;
+  int tiles_w, tiles_h;
+  long long units, upc;         // plane-tiles per X slab (N * tiles * D) and per CTA: a CTA takes the contiguous run [x * upc, (x + 1) * upc)
   int skip;                     // bottleneck knobs (env B200_WG4_SKIP, tools/bench_wgrad_pair.py): 1 = no MMAs, 2 = no TMA after the ring fill
 };
 
@@ -112,15 +113,11 @@ wgrad_tc4_kernel(const Wg4Params g, const __grid_constant__ CUtensorMap tm_p, co
   uint8_t* qbuf = pbuf + kPStages * kPBytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tw = blockIdx.x % g.tiles_w, th = blockIdx.x / g.tiles_w % g.tiles_h;
-  const int rest = blockIdx.x / (g.tiles_w * g.tiles_h);
-  const int n = rest / g.dblocks, db = rest % g.dblocks;
   const int qslab = blockIdx.z;       // which of the two 16-channel X tensors (virtual concat)
-  const int w0 = tw * kTileW, h0 = th * kTileH, d0 = db * g.dseg;
-  const int planes = min(g.dseg, g.D - d0);                       // dY planes d0 .. d0 + planes - 1 belong to this CTA
-  const int q_lo = d0 > 0 ? -1 : 0;                               // X planes (relative to d0) that exist in the volume
-  const int q_hi = d0 + planes < g.D ? planes : planes - 1;
-  const int nd0 = n * g.D + d0;
+  // Work = plane-tiles u = (tile column (n, th, tw), plane d), d fastest.  Every plane-tile of an X slab adds into the SAME dW, so a
+  // CTA takes a contiguous run of u whatever tile columns it crosses — 148 (or 74 + 74) equal shares instead of 128 CTAs of whole
+  // d-blocks — and walks it as segments (one per tile column touched), each with its own two halo planes of X.
+  const long long u_begin = (long long)blockIdx.x * g.upc, u_end = min(u_begin + g.upc, g.units);
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kQStages; ++i) { tc::mbar_init(q_full(i), 1); tc::mbar_init(q_empty(i), 1); }
@@ -147,34 +144,45 @@ wgrad_tc4_kernel(const Wg4Params g, const __grid_constant__ CUtensorMap tm_p, co
     }
     int pst = 0, qst = 0;
     uint32_t pph = 0, qph = 0;
-    for (int i = 0; i <= planes + 1; ++i) {
-      if (i < planes) {
-        tc::mbar_wait(p_empty(pst), pph ^ 1u);
-        if (tc::elect_one()) {
-          if ((g.skip & 2) && i >= kPStages) {
-            tc::mbar_arrive(p_full(pst));
-          } else {
-            tc::mbar_arrive_expect_tx(p_full(pst), kPBytes);
-            load_4d(tc::smem_u32(pbuf + pst * kPBytes), &tm_p, 0, w0 >> 1, h0, nd0 + i, p_full(pst));
+    long long fed = 0;                // planes of either operand issued so far (knob B200_WG4_SKIP & 2)
+    for (long long u = u_begin; u < u_end;) {
+      const long long col = u / g.D;
+      const int d0 = (int)(u - col * g.D), planes = (int)min((long long)(g.D - d0), u_end - u);
+      const int tw = (int)(col % g.tiles_w), th = (int)(col / g.tiles_w % g.tiles_h), n = (int)(col / ((long long)g.tiles_w * g.tiles_h));
+      const int w0 = tw * kTileW, h0 = th * kTileH, nd0 = n * g.D + d0;
+      const int q_lo = d0 > 0 ? -1 : 0;                               // X planes (relative to d0) that exist in the volume
+      const int q_hi = d0 + planes < g.D ? planes : planes - 1;
+      for (int i = 0; i <= planes + 1; ++i) {
+        if (i < planes) {
+          tc::mbar_wait(p_empty(pst), pph ^ 1u);
+          if (tc::elect_one()) {
+            if ((g.skip & 2) && fed >= kPStages) {
+              tc::mbar_arrive(p_full(pst));
+            } else {
+              tc::mbar_arrive_expect_tx(p_full(pst), kPBytes);
+              load_4d(tc::smem_u32(pbuf + pst * kPBytes), &tm_p, 0, w0 >> 1, h0, nd0 + i, p_full(pst));
+            }
           }
+          __syncwarp();
+          if (++pst == kPStages) { pst = 0; pph ^= 1u; }
         }
-        __syncwarp();
-        if (++pst == kPStages) { pst = 0; pph ^= 1u; }
-      }
-      const int q = i - 1;
-      if (q >= q_lo && q <= q_hi) {
-        tc::mbar_wait(q_empty(qst), qph ^ 1u);
-        if (tc::elect_one()) {
-          if ((g.skip & 2) && i >= kPStages) {
-            tc::mbar_arrive(q_full(qst));
-          } else {
-            tc::mbar_arrive_expect_tx(q_full(qst), kQBytes);
-            load_4d(tc::smem_u32(qbuf + qst * kQStageBytes), tq, 0, (w0 >> 1) - 1, h0 - 1, nd0 + q, q_full(qst));
+        const int q = i - 1;
+        if (q >= q_lo && q <= q_hi) {
+          tc::mbar_wait(q_empty(qst), qph ^ 1u);
+          if (tc::elect_one()) {
+            if ((g.skip & 2) && fed >= kPStages) {
+              tc::mbar_arrive(q_full(qst));
+            } else {
+              tc::mbar_arrive_expect_tx(q_full(qst), kQBytes);
+              load_4d(tc::smem_u32(qbuf + qst * kQStageBytes), tq, 0, (w0 >> 1) - 1, h0 - 1, nd0 + q, q_full(qst));
+            }
           }
+          __syncwarp();
+          if (++qst == kQStages) { qst = 0; qph ^= 1u; }
         }
-        __syncwarp();
-        if (++qst == kQStages) { qst = 0; qph ^= 1u; }
+        ++fed;
       }
+      u += planes;
     }
   } else if (warp == 1) {
     // ===================== MMA issue (whole warp walks the loop, one elected lane issues) =====================
@@ -187,54 +195,63 @@ wgrad_tc4_kernel(const Wg4Params g, const __grid_constant__ CUtensorMap tm_p, co
     constexpr uint32_t kAStep = (2 * kQRowBytes) >> 4, kBStep = (2 * kPRowBytes) >> 4;   // one row pair
     tc::mbar_wait(acc_zero, 0);       // the epilogue warps have zeroed the accumulators: every instruction accumulates
     tc::tc_fence_after();
-    int qst = 0, p_ready = 0;
+    int qst = 0, p_ready = 0;         // p_ready: dY planes waited for so far, over all segments (ring position = p_ready & 3)
     uint32_t qph = 0;
-    for (int q = q_lo; q <= q_hi; ++q) {
-      tc::mbar_wait(q_full(qst), qph);
-      const int need = min(q + 2, planes);
-      while (p_ready < need) {
-        tc::mbar_wait(p_full(p_ready & (kPStages - 1)), (uint32_t)(p_ready >> 2) & 1u);
-        ++p_ready;
-      }
-      tc::tc_fence_after();
-      if (tc::elect_one()) {
-        // dY plane q - kd + 1 meets this X plane through kd; kd_lo .. kd_hi are the planes this CTA owns
-        const int kd_lo = max(0, q + 2 - planes), kd_hi = min(2, q + 1);
-        const uint32_t a_q = a_lo0 + (uint32_t)qst * (kQStageBytes >> 4);
-        uint32_t b_kd[3];
-#pragma unroll
-        for (int kd = 0; kd < 3; ++kd) b_kd[kd] = b_lo0 + (uint32_t)((q + 1 - kd) & (kPStages - 1)) * (kPBytes >> 4);
-        if (g.skip & 1) {
-        } else if (kd_lo == 0 && kd_hi == 2) {
-#pragma unroll 2
-          for (int i = 0; i < kTileH / 2; ++i) {
-#pragma unroll
-            for (int type = 0; type < 2; ++type) {
-              // type 0: X voxel w0 - 1 + 2k + p (one voxel = 32 B into the staged row); type 1: two voxels later
-              const uint64_t ad = ((uint64_t)a_hi << 32) | (a_q + (uint32_t)i * kAStep + (type ? 6u : 2u));
-              const uint32_t boff = (uint32_t)i * kBStep, dcol = tmem_base + (uint32_t)(type * 64);
-              mma_fill(dcol, ad, ((uint64_t)b_hi << 32) | (b_kd[0] + boff), idesc);
-              mma_use(dcol + 128u, ad, ((uint64_t)b_hi << 32) | (b_kd[1] + boff), idesc);
-              mma_last(dcol + 256u, ad, ((uint64_t)b_hi << 32) | (b_kd[2] + boff), idesc);
-            }
-          }
-        } else {
-          for (int i = 0; i < kTileH / 2; ++i) {
-#pragma unroll
-            for (int type = 0; type < 2; ++type) {
-              const uint64_t ad = ((uint64_t)a_hi << 32) | (a_q + (uint32_t)i * kAStep + (type ? 6u : 2u));
-              const uint32_t boff = (uint32_t)i * kBStep, dcol = tmem_base + (uint32_t)(type * 64);
-#pragma unroll
-              for (int kd = 0; kd < 3; ++kd)
-                if (kd >= kd_lo && kd <= kd_hi) mma_plain(dcol + (uint32_t)kd * 128u, ad, ((uint64_t)b_hi << 32) | (b_kd[kd] + boff), idesc);
-            }
-          }
+    for (long long u = u_begin; u < u_end;) {
+      const long long col = u / g.D;
+      const int d0 = (int)(u - col * g.D), planes = (int)min((long long)(g.D - d0), u_end - u);
+      const int q_lo = d0 > 0 ? -1 : 0, q_hi = d0 + planes < g.D ? planes : planes - 1;
+      const int p_base = p_ready;     // ring position of this segment's dY plane 0
+      for (int q = q_lo; q <= q_hi; ++q) {
+        tc::mbar_wait(q_full(qst), qph);
+        const int need = p_base + min(q + 2, planes);
+        while (p_ready < need) {
+          tc::mbar_wait(p_full(p_ready & (kPStages - 1)), (uint32_t)(p_ready >> 2) & 1u);
+          ++p_ready;
         }
-        tc::umma_commit(q_empty(qst));
-        if (q - 1 >= 0 && q - 1 < planes) tc::umma_commit(p_empty((q - 1) & (kPStages - 1)));
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
+          // dY plane q - kd + 1 meets this X plane through kd; kd_lo .. kd_hi are the planes this segment owns
+          const int kd_lo = max(0, q + 2 - planes), kd_hi = min(2, q + 1);
+          const uint32_t a_q = a_lo0 + (uint32_t)qst * (kQStageBytes >> 4);
+          uint32_t b_kd[3];
+#pragma unroll
+          for (int kd = 0; kd < 3; ++kd) b_kd[kd] = b_lo0 + (uint32_t)((p_base + q + 1 - kd) & (kPStages - 1)) * (kPBytes >> 4);
+          if (g.skip & 1) {
+          } else if (kd_lo == 0 && kd_hi == 2) {
+#pragma unroll 2
+            for (int i = 0; i < kTileH / 2; ++i) {
+#pragma unroll
+              for (int type = 0; type < 2; ++type) {
+                // type 0: X voxel w0 - 1 + 2k + p (one voxel = 32 B into the staged row); type 1: two voxels later
+                const uint64_t ad = ((uint64_t)a_hi << 32) | (a_q + (uint32_t)i * kAStep + (type ? 6u : 2u));
+                const uint32_t boff = (uint32_t)i * kBStep, dcol = tmem_base + (uint32_t)(type * 64);
+                mma_fill(dcol, ad, ((uint64_t)b_hi << 32) | (b_kd[0] + boff), idesc);
+                mma_use(dcol + 128u, ad, ((uint64_t)b_hi << 32) | (b_kd[1] + boff), idesc);
+                mma_last(dcol + 256u, ad, ((uint64_t)b_hi << 32) | (b_kd[2] + boff), idesc);
+              }
+            }
+          } else {
+            for (int i = 0; i < kTileH / 2; ++i) {
+#pragma unroll
+              for (int type = 0; type < 2; ++type) {
+                const uint64_t ad = ((uint64_t)a_hi << 32) | (a_q + (uint32_t)i * kAStep + (type ? 6u : 2u));
+                const uint32_t boff = (uint32_t)i * kBStep, dcol = tmem_base + (uint32_t)(type * 64);
+#pragma unroll
+                for (int kd = 0; kd < 3; ++kd)
+                  if (kd >= kd_lo && kd <= kd_hi) mma_plain(dcol + (uint32_t)kd * 128u, ad, ((uint64_t)b_hi << 32) | (b_kd[kd] + boff), idesc);
+              }
+            }
+          }
+          tc::umma_commit(q_empty(qst));
+          if (q - 1 >= 0 && q - 1 < planes) tc::umma_commit(p_empty((p_base + q - 1) & (kPStages - 1)));
+          // a segment that ends at the last plane of the volume has no X plane beyond it: release its last dY plane here
+          if (q == q_hi && q_hi < planes) tc::umma_commit(p_empty((p_base + planes - 1) & (kPStages - 1)));
+        }
+        __syncwarp();
+        if (++qst == kQStages) { qst = 0; qph ^= 1u; }
       }
-      __syncwarp();
-      if (++qst == kQStages) { qst = 0; qph ^= 1u; }
+      u += planes;
     }
     if (tc::elect_one()) tc::umma_commit(acc_done);
     __syncwarp();
@@ -323,28 +340,27 @@ int make_pair_map(CUtensorMap* tm, const void* base, int N, int D, int H, int W,
 
 int g_wg4_on = -1;      // -1: read B200_WGRAD_PAIR on first use
 int g_wg4_dseg = 0;     // forced d-run (tests), 0 = planned
-struct Wg4Plan { int qslabs, dseg, dblocks, tiles_w, tiles_h, spatial; };
+struct Wg4Plan { int qslabs, tiles_w, tiles_h, spatial; long long units, upc; };
 
 Wg4Plan make_plan(int c0, int c1, int N, int D, int H, int W) {
   Wg4Plan pl;
   pl.qslabs = (c0 + c1) / 16;
   pl.tiles_w = (W + kTileW - 1) / kTileW;
   pl.tiles_h = (H + kTileH - 1) / kTileH;
-  const int64_t base = (int64_t)pl.tiles_w * pl.tiles_h * N * pl.qslabs;
-  // one CTA per SM (512 TMEM columns): the d-run minimising CTAs-per-SM x (planes streamed + fixed cost of a CTA: two halo
-  // planes, accumulator zeroing, epilogue); longer runs win ties (fewer partials to fold)
-  int dseg = 1;
-  int64_t best = -1;
-  for (int cand = 1; cand <= D && cand <= kMaxDseg; ++cand) {
-    const int64_t ctas = base * ((D + cand - 1) / cand);
-    const int64_t per_sm = (ctas + B200_NUM_SMS - 1) / B200_NUM_SMS;
-    const int64_t cost = per_sm * (cand + 2 + 4);
-    if (best < 0 || cost <= best) { best = cost; dseg = cand; }
-  }
-  if (g_wg4_dseg > 0) dseg = min(g_wg4_dseg, min(D, kMaxDseg));
-  pl.dseg = dseg;
-  pl.dblocks = (D + dseg - 1) / dseg;
-  pl.spatial = pl.tiles_w * pl.tiles_h * N * pl.dblocks;
+  pl.units = (long long)pl.tiles_w * pl.tiles_h * N * D;
+  // one CTA per SM (512 TMEM columns): the SM budget is shared out among the X slabs and every CTA of a slab takes an equal
+  // contiguous run of plane-tiles (first version: whole d-blocks of whole tile columns, whatever CTA count that gave)
+  // SMs this kernel fills (env B200_WG4_SMS).  It runs on the side stream next to the main chain's data-gradient kernels, and a CTA
+  // owns all 512 TMEM columns of its SM: measured in the 2 x 128^3 step, 128 SMs (20 left to the main chain) 3.771 ms, 136: 3.787,
+  // 148: 3.784 — the kernel alone is 7 % faster on 148
+  static int sm_budget = -1;
+  if (sm_budget < 0) { const char* e = getenv("B200_WG4_SMS"); sm_budget = e ? atoi(e) : 128; if (sm_budget < 1 || sm_budget > B200_NUM_SMS) sm_budget = B200_NUM_SMS; }
+  long long ctas = sm_budget / pl.qslabs;
+  if (ctas < 1) ctas = 1;
+  if (ctas > pl.units) ctas = pl.units;
+  pl.upc = (pl.units + ctas - 1) / ctas;
+  if (g_wg4_dseg > 0) pl.upc = g_wg4_dseg;      // tests: short runs (many CTAs, segments that cross tile columns)
+  pl.spatial = (int)((pl.units + pl.upc - 1) / pl.upc);
   return pl;
 }
 
@@ -382,7 +398,7 @@ int b200_conv3d_wgrad_tc4(const void* x0, int c0, const void* x1, int c1, const 
   Wg4Params g;
   g.partial = (float*)workspace;
   g.N = N; g.D = D; g.H = H; g.W = W;
-  g.dseg = pl.dseg; g.dblocks = pl.dblocks; g.tiles_w = pl.tiles_w; g.tiles_h = pl.tiles_h;
+  g.tiles_w = pl.tiles_w; g.tiles_h = pl.tiles_h; g.units = pl.units; g.upc = pl.upc;
   { const char* e = getenv("B200_WG4_SKIP"); g.skip = e ? atoi(e) : 0; }
   CUtensorMap tm_p, tm_q0, tm_q1;
   int rc = make_pair_map(&tm_p, dy, N, D, H, W, kTileW / 2, kTileH);

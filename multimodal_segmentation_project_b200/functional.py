@@ -389,9 +389,11 @@ def set_conv_rowstream(on: bool) -> None:
     check(_lib.load().b200_set_conv_rowstream(int(bool(on))), "set_conv_rowstream")
 
 
-def _bn_partials(C, device):
+def _bn_partials(C, device, rows=0):
+    """Partial-sum buffer [rows][2][C] of the statistics kernels (at least the b200_bn_stats row count; the first layer's fused
+    statistics write one row per CTA, more than that)."""
     L = _lib.load()
-    return torch.empty(L.b200_bn_partials_bytes(C) // 4, dtype=torch.float32, device=device)
+    return torch.empty(max(L.b200_bn_partials_bytes(C) // 4, rows * 2 * C), dtype=torch.float32, device=device)
 
 
 # --------------------------------------------------------------------------- conv + BN + ReLU + Dropout3d
@@ -431,7 +433,7 @@ class _ConvBNAct(torch.autograd.Function):
         rows = L.b200_conv3d_k3_bnstats_blocks(_dt(x0), impl, c0, c1, Cout, 0, N, D, H, W) if (training and _fuse_bn_stats) else 0
         if rows > 0:
             # convolution and batch statistics in ONE kernel: the conv epilogue emits per-CTA (sum, sum of squares) of (y - bias)
-            partials = _bn_partials(Cout, dev)
+            partials = _bn_partials(Cout, dev, rows)
             conv_out = torch.empty((N, D, H, W, Cout), dtype=x0.dtype, device=dev)
             check(L.b200_conv3d_k3_bnstats(_dt(x0), impl, _ptr(x0), c0, _ptr(x1), c1, _ptr(wpack), _ptr(bias32), _ptr(conv_out), Cout,
                                            N, D, H, W, _ptr(partials), _stream()), "conv3d_k3_bnstats")
@@ -589,7 +591,7 @@ def _conv_and_batch_stats(L, x0, x1, weight, bias, gamma, beta, running_mean, ru
     g32, b32, bias32 = _f32(gamma), _f32(beta), _f32(bias)
     c0, c1 = x0.shape[-1], (0 if x1 is None else x1.shape[-1])
     rows = L.b200_conv3d_k3_bnstats_blocks(_dt(x0), impl, c0, c1, Cout, 0, N, D, H, W) if _fuse_bn_stats else 0
-    partials = _bn_partials(Cout, dev)
+    partials = _bn_partials(Cout, dev, rows)
     if rows > 0:
         conv_out = torch.empty((N, D, H, W, Cout), dtype=x0.dtype, device=dev)
         check(L.b200_conv3d_k3_bnstats(_dt(x0), impl, _ptr(x0), c0, _ptr(x1), c1, _ptr(wpack), _ptr(bias32), _ptr(conv_out), Cout,
