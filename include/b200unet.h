@@ -200,17 +200,6 @@ int b200_maxpool2_bwd(int dtype, const void* x, const void* gy, void* gx, int N,
  * in one pass instead of the pool backward followed by autograd's accumulation kernel */
 int b200_maxpool2_bwd_add(int dtype, const void* x, const void* gy, const void* gskip, void* gx, int N, int D, int H, int W, int C,
                           void* stream);
-/* Backward of [BatchNorm3d + ReLU] -> (skip connection, MaxPool3d(2,2)) — models/unet.py:16-18 feeding :69-71 — in two passes that
- * rebuild the gradient w.r.t. the activation from (x = pre-BN conv output, gskip or NULL, gpool) instead of materialising it:
- * _reduce writes per-block BatchNorm-backward partial sums (its return value = number of partial rows for
- * b200_bn_bwd_finalize_ex, negative = error), _apply writes dx.  bf16, even D/H/W, C/8 a power of two <= 32, no Dropout3d
- * (b200_bn_pool_bwd_supported); otherwise use maxpool2_bwd_add + bn_act_bwd_reduce + bn_act_bwd_apply. */
-int b200_bn_pool_bwd_supported(int dtype, int D, int H, int W, int C);
-int b200_bn_pool_bwd_reduce(int dtype, const void* x, const void* gpool, const void* gskip, const float* scale, const float* shift,
-                            const float* mean, const float* invstd, int N, int D, int H, int W, int C, float* partials, void* stream);
-int b200_bn_pool_bwd_apply(int dtype, const void* x, const void* gpool, const void* gskip, void* dx, const float* scale,
-                           const float* shift, const float* mean, const float* invstd, const float* sums, int training, int N, int D,
-                           int H, int W, int C, void* stream);
 
 /* ---------------------------------------------------------------- ConvTranspose3d(k=2,s=2)  models/unet.py:56-58,79
  * x [N,D,H,W,Cin] -> y [N,2D,2H,2W,Cout]; w is the torch layout [Cin, Cout, 2,2,2] fp32. */

@@ -85,9 +85,6 @@ def _declare(lib) -> None:
         "b200_mri_normalize": (I, [P, P, L, P, P]),
         "b200_label_remap": (I, [P, P, L, P, P, P, I, I, P]),
         "b200_maxpool2_bwd_add": (I, [I, P, P, P, P, I, I, I, I, I, P]),
-        "b200_bn_pool_bwd_supported": (I, [I, I, I, I, I]),
-        "b200_bn_pool_bwd_reduce": (I, [I, P, P, P, P, P, P, P, I, I, I, I, I, P, P]),
-        "b200_bn_pool_bwd_apply": (I, [I, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P]),
         "b200_convt2_fwd": (I, [I, P, P, P, P, I, I, I, I, I, I, P]),
         "b200_convt2_bwd_data": (I, [I, P, P, P, I, I, I, I, I, I, P]),
         "b200_convt2_wgrad_workspace": (L, [I, I, I, I, I, I]),

@@ -541,117 +541,6 @@ maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy, const T* 
   }
 }
 
-// ------------------------------------------------------------------ encoder hand-off backward: pool + skip + BatchNorm in two passes
-// An encoder level ends with y = relu(bn(x)) feeding BOTH the skip connection and MaxPool3d(2,2) (models/unet.py:69-71).  Its
-// backward used to be three passes over the full-resolution tensor: maxpool2_bwd_add (gy = gskip + scatter(gpool): read y and
-// gskip, write gy), bn_act_bwd_reduce (read gy and x) and bn_act_bwd_apply (read gy and x, write dx): 16 B/element.  Here the two
-// BatchNorm passes rebuild gy on the fly from (x, gskip, gpool) — y is recomputed from x with the forward kernel's arithmetic,
-// so the arg-max of every window is the forward pass's — and gy is never written: 4 B/element for the reduction, 6 for the
-// apply.  One thread owns a 2x2x2 window of an 8-channel group: 8 loads of x, 8 of gskip and one of gpool in flight.
-// gy = bf16(gskip + gpool) at the window's arg-max (first maximum in window order, NaN wins: torch's rule) and gskip elsewhere,
-// exactly what maxpool2_bwd_add stores; no Dropout3d (the caller falls back to the three-pass sequence), even D, H, W.
-template <typename T, bool APPLY>
-__global__ void __launch_bounds__(kThreads, 2)
-bn_pool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gpool, const T* __restrict__ gskip, T* __restrict__ dx,
-                   const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
-                   const float* __restrict__ invstd, const float* __restrict__ sums, int training, int N, int D, int H, int W, int C,
-                   float* __restrict__ partials) {
-  extern __shared__ float sred[];  // REDUCE: [threads / CV][2][C]
-  const int OD = D / 2, OH = H / 2, OW = W / 2, CV = C / 8;
-  const int cv = threadIdx.x % CV;            // blockDim.x and the grid stride are multiples of CV: a thread keeps its channel group
-  float sc[8], sh[8], mu[8], s0[8], k1[8], a0[8], a1[8];
-  load8(scale, cv, sc); load8(shift, cv, sh); load8(mean, cv, mu);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) a0[k] = a1[k] = s0[k] = k1[k] = 0.f;
-  if (APPLY) {
-    float is[8];
-    load8(sums, cv, s0); load8(sums + C, cv, k1); load8(invstd, cv, is);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) k1[k] *= is[k];
-  }
-  const int64_t total = (int64_t)N * OD * OH * OW * CV;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t t = i / CV;
-    const int ow = (int)(t % OW); t /= OW;
-    const int oh = (int)(t % OH); t /= OH;
-    const int od = (int)(t % OD);
-    const int n = (int)(t / OD);
-    const int64_t row0 = (((int64_t)n * D + 2 * od) * H + 2 * oh) * W + 2 * ow;
-    const int64_t orow = (((int64_t)n * OD + od) * OH + oh) * OW + ow;
-    Vec8<T> xv[8], gv[8], gp;
-#pragma unroll
-    for (int p = 0; p < 8; ++p) xv[p].load(x + (row0 + ((int64_t)(p >> 2) * H + ((p >> 1) & 1)) * W + (p & 1)) * C + cv * 8);
-    gp.load(gpool + orow * C + cv * 8);
-    if (gskip) {
-#pragma unroll
-      for (int p = 0; p < 8; ++p) gv[p].load(gskip + (row0 + ((int64_t)(p >> 2) * H + ((p >> 1) & 1)) * W + (p & 1)) * C + cv * 8);
-    }
-    // pass 1: y = relu(bn(x)) of the eight voxels, the window's arg-max and the ReLU mask (bit p*8 + k)
-    float m[8];
-    int arg[8];
-    uint32_t act_lo = 0, act_hi = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { m[k] = -INFINITY; arg[k] = 0; }
-#pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      float f[8];
-      xv[p].get(f);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float pre = to_f32<T>(from_f32<T>(fmaf(f[k] - mu[k], sc[k], sh[k])));
-        const float yv = fmaxf(pre, 0.f);       // fmaxf drops a NaN pre-activation like the forward kernel does
-        if (pre > 0.f) { if (p < 4) act_lo |= 1u << (p * 8 + k); else act_hi |= 1u << ((p - 4) * 8 + k); }
-        if (pool_better(yv, m[k])) { m[k] = yv; arg[k] = p; }
-      }
-    }
-    float gpf[8];
-    gp.get(gpf);
-    // pass 2: gy per voxel, then the reduction terms or dx
-#pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      float f[8], g[8];
-      xv[p].get(f);
-      if (gskip) gv[p].get(g);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float gg = gskip ? g[k] : 0.f;
-        if (arg[k] == p) gg = gskip ? to_f32<T>(from_f32<T>(gg + gpf[k])) : gpf[k];
-        const bool on = ((p < 4 ? act_lo >> (p * 8 + k) : act_hi >> ((p - 4) * 8 + k)) & 1u) != 0;
-        gg = on ? gg : 0.f;
-        const float xc = f[k] - mu[k];
-        if (APPLY) {
-          float tt = gg;
-          if (training) tt -= fmaf(xc, k1[k], s0[k]);
-          g[k] = tt * sc[k];
-        } else {
-          a0[k] += gg;
-          a1[k] = fmaf(gg, xc, a1[k]);
-        }
-      }
-      if (APPLY) {
-        Vec8<T> o;
-        o.set(g);
-        o.store(dx + (row0 + ((int64_t)(p >> 2) * H + ((p >> 1) & 1)) * W + (p & 1)) * C + cv * 8);
-      }
-    }
-  }
-  if (!APPLY) {
-    const int r = threadIdx.x / CV, rows = blockDim.x / CV;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      sred[(r * 2 + 0) * C + cv * 8 + k] = a0[k];
-      sred[(r * 2 + 1) * C + cv * 8 + k] = a1[k];
-    }
-    __syncthreads();
-    for (int q = threadIdx.x; q < 2 * C; q += blockDim.x) {
-      float t = 0.f;
-      for (int rr = 0; rr < rows; ++rr) t += sred[rr * 2 * C + q];
-      if (q >= C) t *= invstd[q - C];
-      partials[(int64_t)blockIdx.x * 2 * C + q] = t;
-    }
-  }
-}
-
 // ------------------------------------------------------------------ nearest resize (F.interpolate default)
 __device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
   const int s = (int)floorf((float)dst * scale);
@@ -1062,41 +951,6 @@ extern "C" int b200_maxpool2_bwd_add(int dtype, const void* x, const void* gy, c
                                      void* stream) {
   B200_REQUIRE(gskip != nullptr, B200_ERR_SHAPE, "maxpool2_bwd_add: null skip gradient");
   return maxpool2_bwd_impl("maxpool2_bwd_add", dtype, x, gy, gskip, gx, N, D, H, W, C, stream);
-}
-
-// Backward of [BatchNorm + ReLU] -> (skip, MaxPool3d(2,2)) in two passes that never materialise the gradient w.r.t. the
-// activation (bn_pool_bwd_kernel).  bf16, even D/H/W, C/8 a power of two <= 32.  _reduce returns the number of partial rows it
-// wrote (-> b200_bn_bwd_finalize_ex) or a negative status.
-extern "C" int b200_bn_pool_bwd_supported(int dtype, int D, int H, int W, int C) {
-  const int CV = C / 8;
-  return dtype == B200_BF16 && C % 8 == 0 && CV >= 1 && CV <= 32 && (CV & (CV - 1)) == 0 && D >= 2 && H >= 2 && W >= 2 && ((D | H | W) & 1) == 0;
-}
-extern "C" int b200_bn_pool_bwd_reduce(int dtype, const void* x, const void* gpool, const void* gskip, const float* scale, const float* shift,
-                                       const float* mean, const float* invstd, int N, int D, int H, int W, int C, float* partials, void* stream) {
-  B200_REQUIRE(b200_bn_pool_bwd_supported(dtype, D, H, W, C), B200_ERR_UNSUPPORTED, "bn_pool_bwd_reduce: unsupported dtype / shape (C=%d, %dx%dx%d)", C, D, H, W);
-  B200_REQUIRE(x && gpool && scale && shift && mean && invstd && partials, B200_ERR_SHAPE, "bn_pool_bwd_reduce: null pointer");
-  const int64_t items = (int64_t)N * (D / 2) * (H / 2) * (W / 2) * (C / 8);
-  const int cap = 8192 / C > 8 ? 8192 / C : 8;
-  int blocks = b200_grid_for(items, kThreads, 2 * B200_NUM_SMS);
-  if (blocks > cap) blocks = cap;
-  if (blocks > kMaxPartialBlocks) blocks = kMaxPartialBlocks;
-  const size_t smem = (size_t)(kThreads / (C / 8)) * 2 * C * sizeof(float);
-  bn_pool_bwd_kernel<__nv_bfloat16, false><<<blocks, kThreads, smem, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)gpool, (const __nv_bfloat16*)gskip, nullptr, scale, shift, mean, invstd, nullptr, 1, N, D, H, W, C, partials);
-  B200_CHECK_LAUNCH("bn_pool_bwd_reduce");
-  return blocks;
-}
-extern "C" int b200_bn_pool_bwd_apply(int dtype, const void* x, const void* gpool, const void* gskip, void* dx, const float* scale,
-                                      const float* shift, const float* mean, const float* invstd, const float* sums, int training, int N, int D,
-                                      int H, int W, int C, void* stream) {
-  B200_REQUIRE(b200_bn_pool_bwd_supported(dtype, D, H, W, C), B200_ERR_UNSUPPORTED, "bn_pool_bwd_apply: unsupported dtype / shape (C=%d, %dx%dx%d)", C, D, H, W);
-  B200_REQUIRE(x && gpool && dx && scale && shift && mean && invstd && sums, B200_ERR_SHAPE, "bn_pool_bwd_apply: null pointer");
-  const int64_t items = (int64_t)N * (D / 2) * (H / 2) * (W / 2) * (C / 8);
-  bn_pool_bwd_kernel<__nv_bfloat16, true><<<b200_grid_for(items, kThreads, 2 * B200_NUM_SMS), kThreads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)gpool, (const __nv_bfloat16*)gskip, (__nv_bfloat16*)dx, scale, shift, mean, invstd, sums, training, N,
-      D, H, W, C, nullptr);
-  B200_CHECK_LAUNCH("bn_pool_bwd_apply");
-  return B200_OK;
 }
 
 extern "C" int b200_nearest_resize_fwd(int dtype, const void* x, void* y, int N, int D, int H, int W, int OD, int OH, int OW,
