@@ -41,7 +41,7 @@ __device__ __forceinline__ uint64_t desc_kmajor_sw32(uint32_t addr, uint32_t sbo
   return d;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 3)
 convt_tc_kernel(const CtcParams p, const __grid_constant__ CUtensorMap tm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
