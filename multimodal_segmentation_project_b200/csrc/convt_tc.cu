@@ -220,10 +220,7 @@ int run(int bwd, const void* act, const float* w, const float* bias, void* out, 
   p.bias = bias; p.out = (bf16*)out;
   p.N = N; p.D = D; p.H = H; p.W = W; p.cin = Cin; p.cout = Cout; p.bwd = bwd;
   if (!bwd) {
-    // N per CTA = a whole number of children, 64 columns where Cout allows it: 2 x 64 TMEM columns per CTA, so that TMEM stops
-    // limiting residency to two CTAs per SM (ncu: the epilogue's stores of one CTA hide nothing for the other) — the input
-    // tile, a quarter of the output's bytes, is then read by 8 * Cout / 64 CTAs, out of L2
-    p.n_tile = Cout >= 64 ? Cout : (64 / Cout) * Cout;
+    p.n_tile = 8 * Cout <= 256 ? 8 * Cout : 256;
     p.nchunks = 8 * Cout / p.n_tile;
     p.kslabs = Cin / 16;
     p.cpc = p.n_tile / Cout;
