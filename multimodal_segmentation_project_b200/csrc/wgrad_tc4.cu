@@ -350,11 +350,13 @@ Wg4Plan make_plan(int c0, int c1, int N, int D, int H, int W) {
   pl.units = (long long)pl.tiles_w * pl.tiles_h * N * D;
   // one CTA per SM (512 TMEM columns): the SM budget is shared out among the X slabs and every CTA of a slab takes an equal
   // contiguous run of plane-tiles (first version: whole d-blocks of whole tile columns, whatever CTA count that gave)
-  // SMs this kernel fills (env B200_WG4_SMS).  It runs on the side stream next to the main chain's data-gradient kernels, and a CTA
-  // owns all 512 TMEM columns of its SM: measured in the 2 x 128^3 step, 128 SMs (20 left to the main chain) 3.771 ms, 136: 3.787,
-  // 148: 3.784 — the kernel alone is 7 % faster on 148
+  // SMs this kernel fills (env B200_WG4_SMS).  It runs on the side stream next to the main chain's data-gradient kernels, a CTA owns
+  // all 512 TMEM columns of its SM, and nothing waits for a weight gradient before the bucket all-reduce / the optimiser: SMs left
+  // to the main chain shorten the critical path.  Measured ms/step of the 2 x 128^3 train step (two boxes, +-0.02 between boxes):
+  // 148 SMs 3.784, 136: 3.787, 128: 3.771 / 3.763, 120: 3.767, 112: 3.727, 104: 3.716 | 96: 3.657, 80: 3.800, 64: 3.744 — the kernel
+  // alone is fastest on 148 (167 vs 180 us at 128)
   static int sm_budget = -1;
-  if (sm_budget < 0) { const char* e = getenv("B200_WG4_SMS"); sm_budget = e ? atoi(e) : 128; if (sm_budget < 1 || sm_budget > B200_NUM_SMS) sm_budget = B200_NUM_SMS; }
+  if (sm_budget < 0) { const char* e = getenv("B200_WG4_SMS"); sm_budget = e ? atoi(e) : 96; if (sm_budget < 1 || sm_budget > B200_NUM_SMS) sm_budget = B200_NUM_SMS; }
   long long ctas = sm_budget / pl.qslabs;
   if (ctas < 1) ctas = 1;
   if (ctas > pl.units) ctas = pl.units;
