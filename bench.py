@@ -214,7 +214,8 @@ def time_step_kernels(dev, peaks):
     tensor_row("decoder.3.c0 fprop (16+16)->16: conv3d_tc4_kernel", _event_time(lambda: F.conv3d_k3_raw(a16, b16, wp, bias, 16, 0, impl=2), flush), gf)
     wpd = F.pack_conv3_weights(w32, _lib.PACK_DGRAD_TC, torch.bfloat16)
     tensor_row("decoder.3.c0 dgrad 16->(16+16): conv3d_tc4_kernel", _event_time(lambda: F.conv3d_k3_raw(a16, None, wpd, None, 16, 16, impl=2), flush), gf)
-    tensor_row("decoder.3.c0 wgrad (16+16)x16: wgrad_tc4_kernel + partial_reduce", _event_time(lambda: F.conv3d_wgrad_raw(a16, b16, o16, want_bias=False), flush), gf)
+    # the weight gradient runs on 96 of the 148 SMs by design (B200_WG4_SMS: the rest carry the main chain it runs beside)
+    tensor_row("decoder.3.c0 wgrad (16+16)x16: wgrad_tc4_kernel on 96 SMs + partial_reduce", _event_time(lambda: F.conv3d_wgrad_raw(a16, b16, o16, want_bias=False), flush), gf)
     w16 = torch.randn(16, 16, 3, 3, 3, device=dev) * 0.05
     wp16 = F.pack_conv3_weights(w16, _lib.PACK_FPROP_TC, torch.bfloat16)
     tensor_row("encoder.0.c1 fprop 16->16: conv3d_tc4_kernel", _event_time(lambda: F.conv3d_k3_raw(a16, None, wp16, bias, 16, 0, impl=2), flush), gf / 2)
