@@ -353,8 +353,8 @@ Wg4Plan make_plan(int c0, int c1, int N, int D, int H, int W) {
   // SMs this kernel fills (env B200_WG4_SMS).  It runs on the side stream next to the main chain's data-gradient kernels, a CTA owns
   // all 512 TMEM columns of its SM, and nothing waits for a weight gradient before the bucket all-reduce / the optimiser: SMs left
   // to the main chain shorten the critical path.  Measured ms/step of the 2 x 128^3 train step (two boxes, +-0.02 between boxes):
-  // 148 SMs 3.784, 136: 3.787, 128: 3.771 / 3.763, 120: 3.767, 112: 3.727, 104: 3.716 | 96: 3.657, 80: 3.800, 64: 3.744 — the kernel
-  // alone is fastest on 148 (167 vs 180 us at 128)
+  // 148 SMs 3.784, 136: 3.787, 128: 3.771 / 3.763, 120: 3.767, 112: 3.727, 104: 3.716 | 96: 3.657, 80: 3.800, 64: 3.744 | 100: 3.679,
+  // 96: 3.685, 88: 3.762 (tools/time_step.py) — the kernel alone is fastest on 148 (167 vs 180 us at 128, 230 at 96)
   static int sm_budget = -1;
   if (sm_budget < 0) { const char* e = getenv("B200_WG4_SMS"); sm_budget = e ? atoi(e) : 96; if (sm_budget < 1 || sm_budget > B200_NUM_SMS) sm_budget = B200_NUM_SMS; }
   long long ctas = sm_budget / pl.qslabs;
