@@ -15,7 +15,7 @@ from multimodal_segmentation_project_b200.inference import organ_metrics_from_co
 from multimodal_segmentation_project_b200.models.unet import UNet3D
 from oracle import metrics_oracle as OM
 
-SETTINGS = dict(max_examples=30, deadline=None)
+SETTINGS = dict(max_examples=40, deadline=None, derandomize=True)   # the same examples on every run
 
 
 def _case(seed, B, C, D, H, W, absent, ties, nan):
@@ -158,7 +158,7 @@ def test_owned_slabs_partition_the_volume(D, world):
     assert sum(hi - lo for lo, hi in slabs) == D
 
 
-@settings(max_examples=8, deadline=None)
+@settings(max_examples=8, deadline=None, derandomize=True)
 @given(levels=st.integers(1, 4), base=st.sampled_from([4, 8]), cin=st.integers(1, 2), cout=st.integers(1, 4), freeze=st.booleans())
 def test_flat_params_layout_properties(levels, base, cin, cout, freeze):
     """dp.FlatParams on arbitrary `features`: parameters keep their values and order, slices are disjoint, every bucket starts on a
