@@ -835,8 +835,12 @@ class _ConvBNActSkipPool(torch.autograd.Function):
         y, conv_out, stats = _ConvBNAct.forward(ctx, *args)
         pooled = ctx._b200_pooled
         ctx._b200_pooled = None
-        # the pool backward routes by the arg-max of y: saved as a ninth tensor (an output, alive as the skip connection anyway)
-        ctx.save_for_backward(*ctx.to_save, y)
+        # the pool backward routes by the arg-max of y: saved as a ninth tensor (an output, alive as the skip connection anyway).
+        # ctx.to_save is what _ConvBNAct.forward handed to save_for_backward a moment ago (torch.autograd.function.FunctionCtx)
+        saved = getattr(ctx, "to_save", None)
+        if saved is None or len(saved) != 8:
+            raise RuntimeError("_ConvBNActSkipPool: expected the eight tensors _ConvBNAct.forward saves for backward")
+        ctx.save_for_backward(*saved, y)
         return y, pooled, conv_out, stats
 
     @staticmethod
