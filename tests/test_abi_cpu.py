@@ -98,3 +98,42 @@ def test_metric_recipe_host_side_matches_oracle():
             assert od == 0
         else:
             assert np.float32(d / np.float32(v)) == od and np.float32(i / np.float32(v)) == oi
+
+
+def test_host_side_planners_without_gpu():
+    """Pure host functions of the C ABI (no CUDA call): support predicates and workspace planners of the kernels the step picks."""
+    lib = _lib.load()
+    BF16, F32 = _lib.B200_BF16, _lib.B200_F32
+    # BatchNorm apply + pool in one pass: even sizes and an 8-channel group count that divides the 256-thread block
+    ok = lib.b200_bn_act_pool_fwd_supported
+    assert ok(128, 128, 128, 16) == 1 and ok(8, 8, 8, 256) == 1 and ok(4, 6, 6, 8) == 1
+    assert ok(20, 18, 22, 16) == 1 and ok(21, 18, 22, 16) == 0          # odd D: pooled windows would not cover the tensor
+    assert ok(8, 8, 8, 24) == 0 and ok(8, 8, 8, 12) == 0                # 3 groups do not divide the block; C must be a multiple of 8
+    assert ok(1, 8, 8, 16) == 0
+    # weight-gradient workspace: the benchmark's top-level layers run the voxel-pair kernel on B200_WG4_SMS (96) CTAs, each writing
+    # two partial slices [16 ci][27 taps][16 co] fp32 per 16-channel input slab
+    slice_bytes = 16 * 27 * 16 * 4
+    bn = lib.b200_bn_partials_bytes(16)
+    for c0, c1, ctas in ((16, 0, 96), (16, 16, 96)):
+        ws = lib.b200_conv3d_wgrad_workspace(c0, c1, 16, 2, 128, 128, 128)
+        assert ws >= bn + ctas * 2 * slice_bytes and ws % 4 == 0
+    # never smaller for a larger volume; positive for every layer shape of the default U-Net
+    prev = 0
+    for s in (16, 32, 64, 128):
+        ws = lib.b200_conv3d_wgrad_workspace(16, 16, 16, 2, s, s, s)
+        assert ws >= prev > -1
+        prev = ws
+    for c0, c1, co, s in ((1, 0, 16, 128), (16, 0, 32, 64), (64, 64, 64, 32), (128, 0, 256, 8), (256, 0, 256, 8), (128, 128, 128, 16)):
+        assert lib.b200_conv3d_wgrad_workspace(c0, c1, co, 2, s, s, s) > 0
+    # up-convolution weight gradient: dW partials + the bias-gradient partials the same kernel writes (16 floats per CTA and slab)
+    for cin, cout, s in ((32, 16, 64), (64, 32, 32), (128, 64, 16), (256, 128, 8)):
+        ws = lib.b200_convt2_wgrad_workspace(cin, cout, 2, s, s, s)
+        assert ws >= lib.b200_bn_partials_bytes(cout) + 8 * cin * cout * 4
+    # fused-statistics row counts: the first layer (Cin = 1, bf16) reports one row per CTA of its 32 x 8 x 4 tiles, fp32 reports none
+    rows = lib.b200_conv3d_k3_bnstats_blocks(BF16, 2, 1, 0, 16, 0, 2, 128, 128, 128)
+    assert rows == 2 * (128 // 32) * (128 // 8) * (128 // 4)
+    assert lib.b200_conv3d_k3_bnstats_blocks(F32, 2, 1, 0, 16, 0, 2, 128, 128, 128) == 0
+    assert lib.b200_conv3d_k3_bnstats_blocks(BF16, 2, 16, 0, 16, 0, 2, 128, 128, 128) == 148     # persistent row-streaming kernel: one row per SM
+    # packed weight sizes: 27 taps x Cin x Cout bf16 for the tcgen05 layouts
+    assert lib.b200_pack_conv3_bytes(_lib.PACK_FPROP_TC, BF16, 32, 16) == 27 * 16 * 32 * 2
+    assert lib.b200_head_blocks(2, 128 ** 3) == 2 * 148
